@@ -1,0 +1,159 @@
+/*
+ * pigp.h -- C ABI of the B200-native PIGP hot path (libpigp.so).
+ *
+ * Drop-in boundary for the covariance-assembly -> Cholesky -> NLL / dK/dtheta
+ * trace gradient -> posterior path of ogaken1104/stopro.  Every entry point
+ * names the reference interface it replaces (paths relative to the reference
+ * tree).  Plain pointers and sizes only; no torch / JAX types.  All functions
+ * return 0 on success and a negative PIGP_E* code on failure; the message is
+ * available from pigp_last_error() (thread local).  Nothing throws or aborts
+ * across the ABI.  Work is enqueued on the caller's stream (a cudaStream_t
+ * passed as void*, NULL = default stream); "_dev" pointers are device memory,
+ * "_host" pointers are host memory.  Functions whose name ends in _host copy
+ * their inputs to the device and their results back, and synchronise the
+ * stream before returning; the others never synchronise.
+ */
+#ifndef PIGP_H
+#define PIGP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIGP_ABI_VERSION 1
+#define PIGP_MAX_TERMS 8   /* monomials per block (3-D Kfzfz needs 7) */
+#define PIGP_MAX_GROUPS 4  /* hyper-parameter groups per model (ux, uy, uz, pp) */
+#define PIGP_TILE 128      /* row/column padding unit of every factorisation buffer */
+
+enum {
+    PIGP_OK = 0,
+    PIGP_EINVAL = -1,   /* bad argument */
+    PIGP_ECUDA = -2,    /* CUDA runtime error (message in pigp_last_error) */
+    PIGP_ENOMEM = -3,
+    PIGP_ENOTPD = -4    /* informational: a non-positive pivot was met; results are NaN like the reference's */
+};
+
+/* One monomial of a block:  coef * gamma_g * prod_d G_{order[d]}(r_d - r'_d ; l_{g,d}),
+ * G_n = (d/ds)^n exp(-s^2 / (2 l^2)).  order[d] = -1 drops dimension d from the product
+ * (additive kernel form, GP/kernels.py:57-61).  Replaces the nested jax.grad / jax.hessian
+ * operators of GP/gp_2D.py:16-86, GP/gp_3D.py:12-35, GP/gp_1D_laplacian.py:35-46. */
+typedef struct {
+    int32_t group;     /* theta offset of the group = group * (1 + dim): [log gamma, log l_0 ..] (sub_modules/init_modules.py:5-54) */
+    int32_t order[3];
+    double coef;
+} pigp_term;
+
+/* One block function K_AB(r, r') of GP/gp_2D_stokes_independent.py:22-246 /
+ * GP/gp_3D_stokes_independent.py:25-239.  Terms must be sorted by group.
+ * shift_first / shift_second are the periodic-difference wrappers of GP/gp.py:374-410
+ * (setup_kernel_include_difference: first argument; ..._prime: second argument; difdif: both). */
+typedef struct {
+    int32_t n_terms;       /* 0 = the reference's Kzero block */
+    int32_t shift_first;
+    int32_t shift_second;
+    int32_t reserved;
+    pigp_term terms[PIGP_MAX_TERMS];
+} pigp_block_desc;
+
+/* A block-structured covariance matrix: what GPmodel.set_constants (GP/gp.py:263-285) fixes
+ * (sec_tr / sec_te, the jitter rule) together with the class's trainingKs / mixedKs / testKs
+ * table (e.g. GP/gp_poiseuille_independent.py:21-42). */
+typedef struct {
+    int32_t dim;            /* 1, 2 or 3 */
+    int32_t product_form;   /* 1: k = gamma prod_d E_d (kernels.py:64-77); 0: additive, gamma sum_d E_d (kernels.py:57-61) */
+    int32_t n_groups;
+    int32_t symmetric;      /* 1: rows == cols (training / test matrix, GP/gp.py:122-189); 0: rectangular (GP/gp.py:191-211) */
+    int32_t n_row_blocks;
+    int32_t n_col_blocks;   /* ignored when symmetric */
+    const int64_t* sec_row; /* n_row_blocks + 1 offsets (GP/gp.py:258-261 calc_sec) */
+    const int64_t* sec_col; /* ignored when symmetric */
+    const double* pts_row_host; /* [sec_row[last]][dim] row-major; first kernel argument */
+    const double* pts_col_host; /* second kernel argument; ignored when symmetric */
+    const pigp_block_desc* table; /* n_row_blocks x n_col_blocks row-major; symmetric plans read entries (i, j >= i) only,
+                                     first argument = block i points, second = block j points, as Ks[i][j-i] in GP/gp.py:140 */
+    double lbox[3];         /* periodic shift vector (self.lbox) */
+    int32_t noise_lo_block; /* index_optimize_noise[0], or -1: plain jitter (GP/gp.py:23-42) */
+    int32_t noise_hi_block; /* index_optimize_noise[-1]: diagonal add-on is 1 before the range, exp(noise) inside, eps after (GP/gp.py:44-70) */
+} pigp_plan_desc;
+
+typedef struct pigp_plan pigp_plan;
+typedef struct pigp_solver pigp_solver;
+
+enum { PIGP_LAYOUT_FULL = 0, PIGP_LAYOUT_LOWER = 1 };
+
+int pigp_abi_version(void);
+const char* pigp_last_error(void);
+
+/* Device selection for everything created afterwards by this thread (cudaSetDevice). */
+int pigp_set_device(int device);
+
+/* --- plans ------------------------------------------------------------------------------- */
+int pigp_plan_create(const pigp_plan_desc* desc, pigp_plan** out);
+void pigp_plan_destroy(pigp_plan* plan);
+int64_t pigp_plan_rows(const pigp_plan* plan);
+int64_t pigp_plan_cols(const pigp_plan* plan);
+int32_t pigp_plan_theta_len(const pigp_plan* plan); /* n_groups*(1+dim) (+1 when noise is optimised) */
+/* Replace the coordinates (same block sizes); side 0 = rows / first argument, 1 = columns. Async H2D on stream. */
+int pigp_plan_set_points_host(pigp_plan* plan, int side, const double* pts_host, void* stream);
+
+/* trainingK_all / mixedK_all / testK_all (GP/gp.py:287-306): K_dev[row * ld + col], row-major.
+ * add_diag != 0 also applies add_eps_to_sigma (GP/gp.py:23-70) -- symmetric plans only. */
+int pigp_assemble(const pigp_plan* plan, const double* theta_dev, double eps, int add_diag,
+                  double* K_dev, int64_t ld, int layout, void* stream);
+int pigp_assemble_host(pigp_plan* plan, const double* theta_host, double eps, int add_diag,
+                       double* K_host, int layout);
+
+/* --- solver: factorisation workspace bound to a training plan ----------------------------- */
+int pigp_solver_create(pigp_plan* training_plan, pigp_solver** out);
+void pigp_solver_destroy(pigp_solver* s);
+
+/* trainingFunction_all (GP/gp.py:213-224, logpGP :72-89): NLL = 0.5 |L^-1 y|^2 + sum log L_ii + 0.5 n log 2pi.
+ * out_dev[0] = NLL.  info_dev (may be NULL): 0, or 1-based index of the first non-positive pivot. */
+int pigp_nll(pigp_solver* s, const double* theta_dev, const double* y_dev, double eps,
+             double* out_dev, int32_t* info_dev, void* stream);
+/* NLL and d_trainingFunction_all (GP/gp.py:412-488) from one factorisation:
+ * grad[p] = 0.5 * sum_jk (K^-1 - alpha alpha^T)_jk dK_jk/dtheta_p.  The +sum(theta) prior of
+ * sub_modules/loss_modules.py:5-13 and the +1.0 of d_logposterior (GP/gp.py:491-493) stay with the caller. */
+int pigp_nll_grad(pigp_solver* s, const double* theta_dev, const double* y_dev, double eps,
+                  double* nll_dev, double* grad_dev, int32_t* info_dev, void* stream);
+/* Host-buffer variant: the call a user of the reference makes every optimiser step
+ * (func(theta, r_train, delta_y, eps), solver/optimizers.py:173-176).  pts_host may be NULL to keep the
+ * plan's coordinates; otherwise they are re-uploaded.  want_grad = 0 skips the gradient. */
+int pigp_nll_grad_host(pigp_solver* s, const double* theta_host, const double* pts_host, const double* y_host,
+                       double eps, int want_grad, double* nll_host, double* grad_host, int32_t* info_host);
+
+/* predictingFunction_all (GP/gp.py:226-256, postGP :91-120).  mixed: rows = test points, cols = training points;
+ * test: symmetric plan over the test points.  mu_dev[M] = K_ab K_bb^-1 y (mu_test is added by the caller);
+ * cov_dev: full M x M posterior covariance K_aa - V^T V (ld = M) when want_full_cov, else its diagonal (M). */
+int pigp_predict(pigp_solver* s, const pigp_plan* mixed, const pigp_plan* test, const double* theta_dev,
+                 const double* y_dev, double eps, double* mu_dev, double* cov_dev, int want_full_cov,
+                 int32_t* info_dev, void* stream);
+int pigp_predict_host(pigp_solver* s, pigp_plan* mixed, pigp_plan* test, const double* theta_host,
+                      const double* y_host, double eps, double* mu_host, double* cov_host, int want_full_cov,
+                      int32_t* info_host);
+
+/* --- building blocks exposed for tests and benchmarks (device pointers, n multiple of PIGP_TILE) --- */
+/* In-place lower Cholesky of the leading n x n of A (row-major, ld), applying L^-T to the m_extra rows below it
+ * (jnp.linalg.cholesky + jnp.linalg.solve of GP/gp.py:83-84, :106-118).  invd_dev: n/128 inverse diagonal tiles
+ * (128*128 doubles each), workspace output. */
+int pigp_potrf_lower(double* A_dev, int64_t ld, int64_t n, int64_t m_extra, double* invd_dev,
+                     int32_t* info_dev, void* stream);
+/* K^-1 (lower triangle, into X_dev) from the factor L (lower of L_dev) -- replaces solve(L.T, solve(L, I)),
+ * GP/gp.py:431-432.  W_dev receives L^-1 (lower); its upper triangle is scratch. X_dev may alias L_dev. */
+int pigp_potri_lower(const double* L_dev, int64_t ld, int64_t n, const double* invd_dev, double* W_dev,
+                     double* X_dev, void* stream);
+/* C[MxN] = alpha * A * B^T + beta * C with A(m,k), B(n,k); *_kcontig selects which index is contiguous.
+ * M, N multiples of 128, K multiple of 16.  lower_only skips tiles above the diagonal. */
+int pigp_dgemm(int M, int N, int K, double alpha, const double* A_dev, int64_t lda, int a_kcontig,
+               const double* B_dev, int64_t ldb, int b_kcontig, double beta, double* C_dev, int64_t ldc,
+               int lower_only, void* stream);
+
+/* Kernel launches issued by this library since load (all threads); for bench.py's gpu_launches. */
+int64_t pigp_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIGP_H */

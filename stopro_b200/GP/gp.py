@@ -1,0 +1,225 @@
+"""GPmodel: the reference's base-class interface (GP/gp.py) over the CUDA path.
+
+Same public methods, argument meaning and failure behaviour as /root/reference/GP/gp.py:
+  set_constants :263-285, trainingK_all / mixedK_all / testK_all :287-306, trainingFunction_all :213-224,
+  predictingFunction_all :226-256, d_trainingFunction_all :412-488, d_logposterior :491-493,
+  setup_Ks_dKdtheta :322-330 (kept as a no-op: dK/dtheta is evaluated in closed form inside the gradient kernel).
+Inputs are lists of per-variable point arrays, flat delta_y and a log-space theta; outputs are numpy float64.
+A non-positive-definite K gives NaN (as jnp.linalg.cholesky does), never an exception.
+
+A model is a list of *observables* per training / test block (see stopro_b200.operators); the block functions of
+the reference's library (Kuxux, Kfxdiv, Kuxdifux, ...) are available by name through ``model.K<a><b>(r, rp, theta)``.
+"""
+import numpy as np
+
+from .. import _lib, operators
+from ..plan import Plan, Solver
+
+
+class GPmodel:
+    #: names of the observables per training / test block, in block order; set by subclasses
+    train_observables = ()
+    test_observables = ()
+    system = "stokes"  # "stokes" | "scalar"
+
+    def __init__(self, Kernel=None, index_optimize_noise=None, lbox=None):
+        if Kernel is None:
+            raise ValueError("Kernel is required (use stopro_b200.GP.kernels.define_kernel)")
+        self.Kernel = Kernel
+        self.dim = Kernel.input_dim
+        self.product_form = Kernel.product_form
+        self.index_optimize_noise = index_optimize_noise if index_optimize_noise else False
+        self.lbox = None if lbox is None else np.asarray(lbox, dtype=np.float64)
+        if self.system == "stokes":
+            self._obs, self._fields = operators.stokes_observables(self.dim)
+        else:
+            self._obs, self._fields = operators.scalar_observables(self.dim)
+        self.n_kernel_theta = len(self._fields) * (1 + self.dim)
+        self._plans = {}
+        self._solver = None
+        self._cache = None  # (theta bytes, y id, eps) -> (nll, grad)
+
+    # ------------------------------------------------------------------ bookkeeping (gp.py:258-285)
+    @staticmethod
+    def calc_sec(pts):
+        return np.concatenate([np.zeros(1, dtype=int), np.cumsum([len(x) for x in pts])])
+
+    def set_constants(self, *args, only_training=False):
+        if only_training:
+            r_train, delta_y_train, eps = args
+        else:
+            r_test, mu_test, r_train, delta_y_train, eps = args
+            self.num_te = len(r_test)
+            self.sec_te = self.calc_sec(r_test)
+        self.num_tr = len(r_train)
+        self.sec_tr = self.calc_sec(r_train)
+        self._training_plan(r_train)
+        if not only_training:
+            self._mixed_plan(r_test, r_train)
+            self._test_plan(r_test)
+
+    def split_hyp_and_noise(self, theta):
+        theta = np.asarray(theta, dtype=np.float64)
+        if self.index_optimize_noise:
+            return theta[:-1], theta[-1]
+        return theta, None
+
+    def setup_Ks_dKdtheta(self):
+        """Kept for call compatibility (gp.py:322-330); nothing to build."""
+        return None
+
+    # ------------------------------------------------------------------ plans
+    def _observables(self, names):
+        return [self._obs[n] for n in names]
+
+    def _plan(self, key, build, row_pts, col_pts=None):
+        plan = self._plans.get(key)
+        sizes = tuple(len(p) for p in row_pts) + ((-1,) + tuple(len(p) for p in col_pts) if col_pts is not None else ())
+        if plan is not None and plan._sizes == sizes:
+            if not plan.same_points(row_pts, col_pts):
+                plan.set_points(0, row_pts)
+                if col_pts is not None:
+                    plan.set_points(1, col_pts)
+                self._cache = None
+            return plan
+        if plan is not None:
+            if key == "train" and self._solver is not None:
+                self._solver.close()
+                self._solver = None
+            plan.close()
+        plan = build()
+        plan._sizes = sizes
+        self._plans[key] = plan
+        self._cache = None
+        return plan
+
+    def _training_plan(self, r_train):
+        names = self.train_observables[:len(r_train)]
+        if len(names) != len(r_train):
+            raise ValueError(f"{type(self).__name__} has {len(self.train_observables)} training blocks, got {len(r_train)} point sets")
+        return self._plan("train", lambda: Plan(self.dim, self.product_form, self._fields, self._observables(names), r_train,
+                                                lbox=self.lbox, noise_blocks=self.index_optimize_noise or None), r_train)
+
+    def _mixed_plan(self, r_test, r_train):
+        tr = self.train_observables[:len(r_train)]
+        te = self.test_observables[:len(r_test)]
+        return self._plan("mixed", lambda: Plan(self.dim, self.product_form, self._fields, self._observables(te), r_test,
+                                                self._observables(tr), r_train, lbox=self.lbox), r_test, r_train)
+
+    def _test_plan(self, r_test):
+        te = self.test_observables[:len(r_test)]
+        return self._plan("test", lambda: Plan(self.dim, self.product_form, self._fields, self._observables(te), r_test,
+                                               lbox=self.lbox), r_test)
+
+    def _solver_for(self, r_train):
+        plan = self._training_plan(r_train)
+        if self._solver is None or self._solver.plan is not plan:
+            if self._solver is not None:
+                self._solver.close()
+            self._solver = Solver(plan)
+        return self._solver
+
+    def _kernel_theta(self, theta, plan):
+        th = np.asarray(theta, dtype=np.float64).ravel()
+        if th.size == plan.theta_len - 1 and self.index_optimize_noise:
+            th = np.append(th, 0.0)  # builders take theta without the noise entry (gp.py:221-222)
+        return th
+
+    # ------------------------------------------------------------------ covariance builders (gp.py:287-306)
+    def trainingK_all(self, theta, train_pts):
+        plan = self._training_plan(train_pts)
+        return plan.assemble_host(self._kernel_theta(theta, plan), 0.0, False)
+
+    def mixedK_all(self, theta, test_pts, train_pts):
+        plan = self._mixed_plan(test_pts, train_pts)
+        return plan.assemble_host(np.asarray(theta, dtype=np.float64)[:self.n_kernel_theta], 0.0, False)
+
+    def testK_all(self, theta, test_pts):
+        plan = self._test_plan(test_pts)
+        return plan.assemble_host(np.asarray(theta, dtype=np.float64)[:self.n_kernel_theta], 0.0, False)
+
+    def add_eps_to_sigma(self, Sigma, eps, noise_parameter=None):
+        """gp.py:23-70 on a host matrix (the fused device path adds the diagonal inside the assembly kernel)."""
+        n = len(Sigma)
+        d = np.ones(n)
+        if self.index_optimize_noise:
+            lo = self.sec_tr[self.index_optimize_noise[0]]
+            hi = self.sec_tr[self.index_optimize_noise[-1] + 1]
+            d[lo:hi] *= np.exp(noise_parameter)
+            d[hi:] *= eps
+        else:
+            d *= eps
+        return Sigma + np.diag(d)
+
+    def training_sigma(self, theta, train_pts, eps):
+        """trainingK_all + add_eps_to_sigma in one kernel (gp.py:221-223)."""
+        plan = self._training_plan(train_pts)
+        return plan.assemble_host(theta, eps, True)
+
+    # ------------------------------------------------------------------ likelihood and gradient
+    def value_and_grad(self, theta, r, delta_y, eps, want_grad=True):
+        """(NLL, dNLL/dtheta) from ONE factorisation; cached so that func(theta) followed by dfunc(theta)
+        (solver/optimizers.py:148-150) costs one evaluation."""
+        th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64).ravel())
+        y = np.ascontiguousarray(np.asarray(delta_y, dtype=np.float64).ravel())
+        solver = self._solver_for(r)
+        key = (th.tobytes(), y.tobytes(), float(eps))
+        if self._cache is not None and self._cache[0] == key and (self._cache[2] is not None or not want_grad):
+            return self._cache[1], self._cache[2]
+        nll, grad, _info = solver.nll_grad_host(th, y, eps, want_grad=want_grad)
+        self._cache = (key, nll, grad)
+        return nll, grad
+
+    def trainingFunction_all(self, theta, *args):
+        r, delta_y, eps = args
+        return self.value_and_grad(theta, r, delta_y, eps, want_grad=False)[0]
+
+    def d_trainingFunction_all(self, theta, *args):
+        r, delta_y, eps = args
+        return self.value_and_grad(theta, r, delta_y, eps, want_grad=True)[1].copy()
+
+    def d_logposterior(self, theta, *args):
+        return self.d_trainingFunction_all(theta, *args) + 1.0  # gradient of the sum(theta) prior (gp.py:491-493)
+
+    # ------------------------------------------------------------------ posterior (gp.py:226-256)
+    def predictingFunction_all(self, theta, *args, full_cov=True):
+        r_test, mu_test, r_train, delta_y_train, eps = args
+        solver = self._solver_for(r_train)
+        mixed = self._mixed_plan(r_test, r_train)
+        test = self._test_plan(r_test)
+        mu, cov, _info = solver.predict_host(mixed, test, theta, delta_y_train, eps, full_cov=full_cov)
+        self._cache = None
+        mus, covs, lo = [], [], 0
+        for i in range(len(r_test)):
+            hi = lo + len(r_test[i])
+            mus.append(mu[lo:hi] + np.asarray(mu_test[i], dtype=np.float64))
+            covs.append(cov[lo:hi, lo:hi].copy() if full_cov else cov[lo:hi].copy())
+            lo = hi
+        return mus, covs
+
+    # ------------------------------------------------------------------ named blocks of the reference's library
+    def __getattr__(self, name):
+        # K<a><b>(r, rp, theta): cov(a(r), b(rp)), e.g. Kuxfx, Kfxdiv, Kdifuxdifux, Kpdifp (gp_2D_stokes_independent.py:22-246)
+        if name.startswith("K") and not name.startswith("Kernel") and "_obs" in self.__dict__:
+            rest = name[1:]
+            for a in sorted(self._obs, key=len, reverse=True):
+                if rest.startswith(a) and rest[len(a):] in self._obs:
+                    oa, ob = self._obs[a], self._obs[rest[len(a):]]
+
+                    def block(r, rp, theta, _oa=oa, _ob=ob):
+                        plan = Plan(self.dim, self.product_form, self._fields, [_oa], [r], [_ob], [rp], lbox=self.lbox)
+                        try:
+                            return plan.assemble_host(np.asarray(theta, dtype=np.float64)[:self.n_kernel_theta])
+                        finally:
+                            plan.close()
+
+                    return block
+        raise AttributeError(name)
+
+    def close(self):
+        if self._solver is not None:
+            self._solver.close()
+            self._solver = None
+        for p in self._plans.values():
+            p.close()
+        self._plans = {}

@@ -1,0 +1,111 @@
+// Internal declarations shared by the translation units of libpigp.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/pigp.h"
+
+namespace pigp {
+
+constexpr int TILE = PIGP_TILE;        // 128: padding unit and GEMM tile
+constexpr int ASM_TR = 32;             // assembly tile rows
+constexpr int ASM_TC = 128;            // assembly tile cols
+constexpr int MAX_THETA = PIGP_MAX_GROUPS * 4 + 1;  // 16 kernel hyper-parameters + noise
+
+void set_error(const std::string& msg);
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define PIGP_CUDA(expr)                                                                         \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            pigp::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+            return PIGP_ECUDA;                                                                  \
+        }                                                                                       \
+    } while (0)
+
+#define PIGP_TRY(expr)                 \
+    do {                               \
+        int _rc = (expr);              \
+        if (_rc != PIGP_OK) return _rc; \
+    } while (0)
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// One rectangle of the output matrix, evaluated by one CTA of the assembly / gradient kernels.
+struct AsmTile {
+    int32_t row0, col0;    // output coordinates of the tile origin
+    int32_t nrows, ncols;  // extent (<= ASM_TR x ASM_TC)
+    int32_t desc;          // block descriptor index, -1 = zero fill (Kzero or padding)
+    int32_t flags;         // ASM_* bits
+};
+enum {
+    ASM_SWAP = 1,   // first kernel argument is the COLUMN point (lower half of an upper-table block)
+    ASM_LOWER = 2,  // write / weigh only entries with row >= col
+    ASM_PAD = 4,    // padding region: zero, 1.0 on the diagonal
+};
+
+}  // namespace pigp
+
+struct pigp_plan {
+    int dim = 0, product_form = 1, n_groups = 0, symmetric = 0;
+    int n_row_blocks = 0, n_col_blocks = 0;
+    std::vector<int64_t> sec_row, sec_col;
+    int64_t rows = 0, cols = 0;
+    double lbox[3] = {0, 0, 0};
+    int noise_lo_block = -1, noise_hi_block = -1;
+    int64_t noise_lo = 0, noise_hi = 0;  // row range carrying exp(noise)
+    int theta_len = 0;                   // incl. noise
+    int device = 0;
+    std::vector<pigp_block_desc> table;  // host copy, n_row_blocks x n_col_blocks
+    // device state
+    double* d_pts_row = nullptr;  // [dim][rows] (structure of arrays)
+    double* d_pts_col = nullptr;  // [dim][cols]; == d_pts_row when symmetric
+    pigp_block_desc* d_table = nullptr;
+    pigp::AsmTile* d_tiles_full = nullptr;
+    int64_t n_tiles_full = 0;
+    pigp::AsmTile* d_tiles_lower = nullptr;  // symmetric plans only
+    int64_t n_tiles_lower = 0;
+    double* d_theta_stage = nullptr;  // MAX_THETA doubles, for the _host entry points
+    double* h_pin = nullptr;          // pinned staging
+    int64_t h_pin_bytes = 0;
+};
+
+namespace pigp {
+
+// ---- assembly / gradient (pigp_assemble.cu)
+int launch_assemble(const pigp_plan* p, const AsmTile* tiles, int64_t n_tiles, const double* theta_dev, double eps,
+                    int add_diag, double* K, int64_t ld, cudaStream_t st);
+// zero-fill + unit diagonal for rows/cols outside the plan's extent, up to rows_pad x cols_pad
+int launch_pad(double* K, int64_t ld, int64_t rows, int64_t cols, int64_t rows_pad, int64_t cols_pad, int unit_diag,
+               int lower_only, cudaStream_t st);
+// partials[n_tiles_lower][MAX_THETA] <- per-tile sums of (X - alpha alpha^T) * dK/dtheta ; then reduce into grad
+int launch_grad(const pigp_plan* p, const double* theta_dev, const double* X, int64_t ld, const double* alpha,
+                double* partials, double* grad_out, cudaStream_t st);
+
+// ---- dense linear algebra (pigp_dense.cu)
+struct GemmDesc {
+    int M, N, K;
+    double alpha, beta;
+    const double* A; int64_t lda; int a_kcontig;
+    const double* B; int64_t ldb; int b_kcontig;
+    double* C; int64_t ldc;
+    int lower_only;  // skip tiles with tn > tm
+    int kmode;       // 0: all k; 1: k_tile >= m_tile; 2: k_tile <= m_tile
+};
+int launch_gemm(const GemmDesc& g, cudaStream_t st);
+int potrf_lower(double* A, int64_t ld, int64_t n, int64_t m_extra, double* invd, int32_t* info, cudaStream_t st);
+int potri_lower(const double* L, int64_t ld, int64_t n, const double* invd, double* W, double* X, cudaStream_t st);
+// out[0] = sum_{i<n} log A[i*ld+i]; out[1] = sum_{j<n} v[j]^2  (v = row `vrow` of A)
+int launch_logdet_quad(const double* A, int64_t ld, int64_t n, const double* v, double* out2, cudaStream_t st);
+// y[j] = sum_{i>=j} W[i*ld+j] x[i]   (W lower, n x n): alpha = W^T v
+// part: workspace of ceil(n/1024) * n doubles
+int launch_trmv_lower_t(const double* W, int64_t ld, int64_t n, const double* x, double* y, double* part, cudaStream_t st);
+// y[i] = sum_j A[i*ld+j] x[j], A (m x n) row-major
+int launch_gemv(const double* A, int64_t ld, int64_t m, int64_t n, const double* x, double* y, cudaStream_t st);
+
+}  // namespace pigp

@@ -1,0 +1,182 @@
+"""Python handles over the C ABI: Plan (block-structured covariance) and Solver (factorisation workspace)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, operators
+
+
+def stack_points(pts, dim):
+    """list of (n_i, dim) arrays ((n_i,) when dim == 1) -> (N, dim) float64 C-contiguous, plus section offsets
+    (GP/gp.py:258-261 calc_sec)."""
+    arrs = []
+    for p in pts:
+        a = np.asarray(p, dtype=np.float64)
+        if dim == 1:
+            a = a.reshape(-1, 1)
+        if a.ndim != 2 or a.shape[1] != dim:
+            raise ValueError(f"expected points of shape (n, {dim}), got {a.shape}")
+        arrs.append(a)
+    sec = np.concatenate([[0], np.cumsum([len(a) for a in arrs])]).astype(np.int64)
+    flat = np.ascontiguousarray(np.concatenate(arrs, axis=0)) if arrs else np.zeros((0, dim))
+    return flat, sec
+
+
+def _ptr(a, typ=C.c_double):
+    return a.ctypes.data_as(C.POINTER(typ))
+
+
+class Plan:
+    """A block matrix  [cov(A_i(r_i), B_j(r'_j))]_{ij}  bound to its point sets."""
+
+    def __init__(self, dim, product_form, fields, row_obs, row_pts, col_obs=None, col_pts=None, lbox=None,
+                 noise_blocks=None):
+        self.dim, self.product_form, self.fields = dim, bool(product_form), list(fields)
+        self.symmetric = col_obs is None
+        self.row_obs, self.col_obs = list(row_obs), (list(row_obs) if col_obs is None else list(col_obs))
+        self._rows, self.sec_row = stack_points(row_pts, dim)
+        if self.symmetric:
+            self._cols, self.sec_col = self._rows, self.sec_row
+        else:
+            self._cols, self.sec_col = stack_points(col_pts, dim)
+        if len(self.row_obs) != len(self.sec_row) - 1 or len(self.col_obs) != len(self.sec_col) - 1:
+            raise ValueError("one observable per point block is required")
+        nr, nc = len(self.row_obs), len(self.col_obs)
+        table = (_lib.BlockDesc * (nr * nc))()
+        for i in range(nr):
+            for j in range(nc):
+                if self.symmetric and j < i:
+                    continue
+                table[i * nc + j] = operators.make_desc(self.row_obs[i], self.col_obs[j], self.fields, dim,
+                                                        self.product_form)
+        self._table = table
+        d = _lib.PlanDesc()
+        d.dim, d.product_form, d.n_groups, d.symmetric = dim, int(self.product_form), len(self.fields), int(self.symmetric)
+        d.n_row_blocks, d.n_col_blocks = nr, nc
+        d.sec_row, d.sec_col = _ptr(self.sec_row, C.c_int64), _ptr(self.sec_col, C.c_int64)
+        d.pts_row_host, d.pts_col_host = _ptr(self._rows), _ptr(self._cols)
+        d.table = table
+        lb = np.zeros(3) if lbox is None else np.concatenate([np.asarray(lbox, dtype=np.float64).ravel(), np.zeros(3)])[:3]
+        for k in range(3):
+            d.lbox[k] = float(lb[k])
+        if noise_blocks:
+            d.noise_lo_block, d.noise_hi_block = int(noise_blocks[0]), int(noise_blocks[-1])
+        else:
+            d.noise_lo_block = d.noise_hi_block = -1
+        h = C.c_void_p()
+        _lib.check(_lib.lib().pigp_plan_create(C.byref(d), C.byref(h)))
+        self.handle = h
+        self.rows, self.cols = int(self.sec_row[-1]), int(self.sec_col[-1])
+        self.theta_len = int(_lib.lib().pigp_plan_theta_len(h))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib.lib().pigp_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def same_points(self, row_pts, col_pts=None):
+        def eq(flat, pts):
+            try:
+                a, _ = stack_points(pts, self.dim)
+            except ValueError:
+                return False
+            return a.shape == flat.shape and np.array_equal(a, flat)
+
+        return eq(self._rows, row_pts) and (self.symmetric or eq(self._cols, col_pts))
+
+    def set_points(self, side, pts):
+        flat, sec = stack_points(pts, self.dim)
+        ref_sec = self.sec_row if (side == 0 or self.symmetric) else self.sec_col
+        if not np.array_equal(sec, ref_sec):
+            raise ValueError("block sizes differ from the plan's")
+        _lib.check(_lib.lib().pigp_plan_set_points_host(self.handle, side, flat.ctypes.data, None))
+        if side == 0 or self.symmetric:
+            self._rows = flat
+            if self.symmetric:
+                self._cols = flat
+        else:
+            self._cols = flat
+
+    def _theta(self, theta):
+        th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64).ravel())
+        if th.size != self.theta_len:
+            raise ValueError(f"theta has {th.size} entries, the model needs {self.theta_len}")
+        return th
+
+    def assemble_host(self, theta, eps=0.0, add_diag=False, layout=_lib.LAYOUT_FULL):
+        th = self._theta(theta)
+        K = np.empty((self.rows, self.cols), dtype=np.float64)
+        _lib.check(_lib.lib().pigp_assemble_host(self.handle, th.ctypes.data, float(eps), int(add_diag), K.ctypes.data,
+                                                 int(layout)))
+        return K
+
+    def assemble(self, theta_ptr, eps, add_diag, out_ptr, ld, layout=_lib.LAYOUT_FULL, stream=None):
+        """Device-pointer form (theta_ptr / out_ptr are integers, e.g. torch.Tensor.data_ptr())."""
+        _lib.check(_lib.lib().pigp_assemble(self.handle, theta_ptr, float(eps), int(add_diag), out_ptr, int(ld), int(layout),
+                                            stream))
+
+
+class Solver:
+    def __init__(self, plan):
+        if not plan.symmetric:
+            raise ValueError("Solver needs the symmetric training plan")
+        self.plan = plan
+        h = C.c_void_p()
+        _lib.check(_lib.lib().pigp_solver_create(plan.handle, C.byref(h)))
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib.lib().pigp_solver_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def nll_grad_host(self, theta, y, eps, want_grad=True, pts=None):
+        """One NLL (+ gradient) evaluation with host buffers in and out -> (nll, grad or None, info)."""
+        p = self.plan
+        th = p._theta(theta)
+        yy = np.ascontiguousarray(np.asarray(y, dtype=np.float64).ravel())
+        if yy.size != p.rows:
+            raise ValueError(f"delta_y has {yy.size} entries, the training set has {p.rows}")
+        pts_ptr = None
+        if pts is not None:
+            flat, sec = stack_points(pts, p.dim)
+            if not np.array_equal(sec, p.sec_row):
+                raise ValueError("block sizes differ from the plan's")
+            pts_ptr = flat.ctypes.data
+        nll = C.c_double()
+        grad = np.empty(p.theta_len, dtype=np.float64)
+        info = C.c_int32()
+        _lib.check(_lib.lib().pigp_nll_grad_host(self.handle, th.ctypes.data, pts_ptr, yy.ctypes.data, float(eps),
+                                                 int(want_grad), C.addressof(nll), grad.ctypes.data, C.addressof(info)))
+        return nll.value, (grad if want_grad else None), info.value
+
+    def nll_grad(self, theta_ptr, y_ptr, eps, nll_ptr, grad_ptr, info_ptr=None, stream=None):
+        _lib.check(_lib.lib().pigp_nll_grad(self.handle, theta_ptr, y_ptr, float(eps), nll_ptr, grad_ptr, info_ptr, stream))
+
+    def nll(self, theta_ptr, y_ptr, eps, nll_ptr, info_ptr=None, stream=None):
+        _lib.check(_lib.lib().pigp_nll(self.handle, theta_ptr, y_ptr, float(eps), nll_ptr, info_ptr, stream))
+
+    def predict_host(self, mixed, test, theta, y, eps, full_cov=True):
+        p = self.plan
+        th = p._theta(theta)
+        yy = np.ascontiguousarray(np.asarray(y, dtype=np.float64).ravel())
+        m = mixed.rows
+        mu = np.empty(m, dtype=np.float64)
+        cov = np.empty((m, m) if full_cov else (m,), dtype=np.float64)
+        info = C.c_int32()
+        _lib.check(_lib.lib().pigp_predict_host(self.handle, mixed.handle, test.handle, th.ctypes.data, yy.ctypes.data,
+                                                float(eps), mu.ctypes.data, cov.ctypes.data, int(full_cov),
+                                                C.addressof(info)))
+        return mu, cov, info.value

@@ -1,0 +1,32 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def oracle_for(cfg, backend="closed"):
+    """The CPU oracle (oracle.gp_ref.GPRef) configured like a stopro_b200.synthetic configuration."""
+    from oracle.gp_ref import GPRef
+
+    kw = cfg["model_kwargs"]
+    gp = GPRef(cfg["model"], kernel_form=cfg["kernel"]["kernel_form"], dim=cfg["kernel"]["input_dim"],
+               lbox=kw.get("lbox"), index_optimize_noise=kw.get("index_optimize_noise"), backend=backend)
+    gp.set_constants(cfg["r_test"], cfg["mu_test"], cfg["r_train"], cfg["delta_y"], cfg["eps"])
+    return gp
+
+
+@pytest.fixture(scope="session")
+def cuda_device():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
