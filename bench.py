@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Benchmark of the PIGP hot path: NLL + gradient evaluations per second at N = 20k synthetic 2-D Stokes points.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 20000]
+
+One "step" = one negative-log-marginal-likelihood + dK/dtheta-trace-gradient evaluation (assemble K -> Cholesky ->
+log-det / quadratic form -> K^-1 -> fused trace reduction) of the C5 workload of SURVEY.md section 8(d).
+`value` is timed with the inputs resident in HBM through the device-pointer C ABI; `e2e` goes through the
+reference-facing host call (theta, points and delta_y copied host->device and the loss / gradient read back inside
+the timed region, every step).  For N > 1 (torchrun, one rank per GPU) every rank evaluates its own theta on the
+same data -- independent evaluations, no data-path collective -- and the time is the max over ranks.
+`--impl reference` times the CPU restatement of the reference's own algorithm (oracle/, numpy + LAPACK on all host
+cores) on a bounded sample of the same workload.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "NLL+grad evals/s at N=20k"
+UNIT = "evals/s"
+FP64_PEAK_FALLBACK = 36.45  # TFLOP/s, cuBLAS DGEMM 16384^3 on this pool's B200 (profiles/r01_fp64_peak.json)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=20000, help="training points (the metric is quoted at 20000)")
+    ap.add_argument("--cpu-sample-n", type=int, default=4000, help="points of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_eval(n_sample, n_full, repeats=1):
+    """Time the restated reference (oracle.gp_ref.GPRef, reference op sequence: Cholesky, general solves against I,
+    one dense matmul per hyper-parameter -- GP/gp.py:72-89, :412-488) on an n_sample-point instance of the workload
+    and scale by the reference's (7 + 2P) N^3 cost model to n_full.  Returns (evals/s at n_full, seconds per sample)."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import oracle_for
+    from stopro_b200 import synthetic
+
+    cfg = synthetic.stokes2d_scaling(n_sample, n_test=16)
+    ref = oracle_for(cfg)
+    args = (cfg["r_train"], cfg["delta_y"], cfg["eps"])
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        f = ref.trainingFunction_all(cfg["theta0"], *args)      # func(theta)   (solver/optimizers.py:148-150 calls both)
+        g = ref.d_trainingFunction_all(cfg["theta0"], *args)    # dfunc(theta)
+        best = min(best, time.perf_counter() - t0)
+    assert np.isfinite(f) and np.all(np.isfinite(g))
+    scale = (n_full / n_sample) ** 3
+    return 1.0 / (best * scale), best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    times = []
+    for _ in range(args.warmup):
+        cpu_reference_eval(min(args.cpu_sample_n, 1500), args.n)
+    t_all0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, sec = cpu_reference_eval(args.cpu_sample_n, args.n)
+        times.append(sec)
+    wall = time.perf_counter() - t_all0
+    sec = sum(times) / len(times)
+    scale = (args.n / args.cpu_sample_n) ** 3
+    value = 1.0 / (sec * scale)
+    sample = (f"one func+dfunc evaluation per step at N={args.cpu_sample_n} points of the same workload "
+              f"({sec:.2f} s each), scaled to N={args.n} by (N/Ns)^3")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sec * scale, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C5 synthetic 2-D Stokes PIGP, N={args.n}, P=9, product SE (timed on a bounded sample)",
+                   "sample_wall_s": wall},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+        except OSError:
+            self.proc = None
+            return
+        threading.Thread(target=self._read, daemon=True).start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from stopro_b200 import _lib, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    _lib.check(_lib.lib().pigp_set_device(local))
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = synthetic.stokes2d_scaling(args.n, n_test=16)
+    gp = synthetic.make_model(cfg)
+    r_train, y, eps = cfg["r_train"], cfg["delta_y"], cfg["eps"]
+    gp.set_constants(r_train, y, eps, only_training=True)
+    solver = gp._solver_for(r_train)
+    P = solver.plan.theta_len
+    N = solver.plan.rows
+    rng = np.random.default_rng(100 + rank)
+    theta_host = cfg["theta0"] + (0.01 * rng.standard_normal(P) if world > 1 else 0.0)  # one start per rank
+
+    theta = torch.as_tensor(theta_host, device=dev)
+    y_dev = torch.as_tensor(y, device=dev)
+    out = torch.zeros(1 + P, dtype=torch.float64, device=dev)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream or None
+
+    def step_device():
+        solver.nll_grad(theta.data_ptr(), y_dev.data_ptr(), eps, out.data_ptr(), out.data_ptr() + 8, info.data_ptr(), stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = _lib.launch_count()
+    ms_total = timed(step_device, args.steps)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    res = out.cpu().numpy()
+    finite = bool(np.all(np.isfinite(res))) and int(info.item()) == 0
+
+    # e2e: the host call of the reference-facing API (theta, points and delta_y H2D, loss + gradient D2H, each step)
+    pts_flat = np.ascontiguousarray(np.concatenate(r_train, axis=0))
+
+    def step_host():
+        solver.nll_grad_host(theta_host, y, eps, want_grad=True, pts=r_train)
+
+    step_host()
+    ms_e2e = timed(step_host, args.steps)
+    h2d = theta_host.nbytes + pts_flat.nbytes + y.nbytes
+    d2h = 8 * (1 + P) + 4
+
+    # per-kernel-class device time of one step (separate pass; event pairs around every launch)
+    _lib.profile_start()
+    step_device()
+    prof = _lib.profile_stop()
+    gemm = prof["gemm"]
+    step_ms_prof = sum(c["ms"] for c in prof.values())
+
+    # FP64 roofline denominator: measured in-run (cuBLAS DGEMM through torch), else the recorded pool figure
+    peak, peak_src = FP64_PEAK_FALLBACK, "profiles/r01_fp64_peak.json (cuBLAS DGEMM 16384^3)"
+    if rank == 0:
+        try:
+            a = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+            b = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+            torch.matmul(a, b)
+            best = 1e30
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                torch.matmul(a, b)
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            peak, peak_src = 2 * 8192.0 ** 3 / best * 1e-9, "cuBLAS DGEMM 8192^3 measured in this run (burst, best of 3)"
+            del a, b
+        except Exception as exc:  # noqa: BLE001
+            peak_src += f"; in-run measurement failed: {exc}"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    algorithmic_flops = float(N) ** 3  # N^3/3 (POTRF) + 2N^3/3 (K^-1), SURVEY.md section 8(d)
+    achieved = algorithmic_flops / (gemm["ms"] * 1e-3) * 1e-12
+    line = {
+        "metric": METRIC, "value": world * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C5 synthetic 2-D Stokes PIGP (blocks ux,uy,p,fx,fy,div), N={N}, P={P}, product SE, "
+                               f"eps={eps}, logl=log(4/sqrt(N))",
+                   "parallelism": "single GPU" if world == 1 else f"{world} independent evaluations (one theta per rank), no collective",
+                   "l2": f"inputs larger than L2: K and K^-1 are {8 * N * N / 1e9:.1f} GB each, rewritten every step",
+                   "finite": finite},
+        "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "pigp::k_gemm (mma.sync.m8n8k4.f64 / DMMA.8x8x4)",
+                     "peak_source": peak_src,
+                     "algorithmic_flops_per_step": algorithmic_flops,
+                     "executed_tflops": gemm["flops"] / (gemm["ms"] * 1e-3) * 1e-12,
+                     "kernel_ms_per_step": gemm["ms"], "kernel_launches_per_step": gemm["launches"],
+                     "share_of_step": gemm["ms"] / step_ms_prof,
+                     "classes_ms": {k: round(v["ms"], 3) for k, v in prof.items()}},
+        "nll": float(res[0]),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, sec = cpu_reference_eval(args.cpu_sample_n, N)
+        line["cpu_baseline"] = {
+            "value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"one func+dfunc evaluation of the restated reference (oracle/, numpy+LAPACK) at N={args.cpu_sample_n} "
+                      f"points of the same workload: {sec:.2f} s, scaled to N={N} by (N/Ns)^3"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -153,6 +153,14 @@ int pigp_dgemm(int M, int N, int K, double alpha, const double* A_dev, int64_t l
 /* Kernel launches issued by this library since load (all threads); for bench.py's gpu_launches. */
 int64_t pigp_launch_count(void);
 
+/* Per-kernel-class device timing for bench.py's roofline object (not part of the reference interface).
+ * Between start and stop every launch is bracketed by a CUDA event pair on its stream; stop synchronises and
+ * returns, per class, the summed kernel time [ms], the number of launches and (GEMM class) the flops executed
+ * at tile granularity.  Classes: 0 assemble, 1 gemm (DMMA), 2 potf2, 3 gradient, 4 everything else. */
+#define PIGP_PROF_CLASSES 5
+int pigp_profile_start(void);
+int pigp_profile_stop(double* ms_out, int64_t* launches_out, double* flops_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,7 +66,10 @@ _SIGNATURES = {
     "pigp_dgemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64,
                              C.c_int, C.c_double, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "pigp_launch_count": (C.c_int64, []),
+    "pigp_profile_start": (C.c_int, []),
+    "pigp_profile_stop": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
 }
+PROF_CLASSES = ("assemble", "gemm", "potf2", "gradient", "misc")
 EXPORTS = tuple(_SIGNATURES)
 
 
@@ -95,3 +98,15 @@ def check(rc):
 
 def launch_count():
     return int(lib().pigp_launch_count())
+
+
+def profile_start():
+    check(lib().pigp_profile_start())
+
+
+def profile_stop():
+    """-> {class: dict(ms=, launches=, flops=)} for the launches since profile_start()."""
+    n = len(PROF_CLASSES)
+    ms, cnt, fl = (C.c_double * n)(), (C.c_int64 * n)(), (C.c_double * n)()
+    check(lib().pigp_profile_stop(ms, cnt, fl))
+    return {name: dict(ms=ms[i], launches=int(cnt[i]), flops=fl[i]) for i, name in enumerate(PROF_CLASSES)}

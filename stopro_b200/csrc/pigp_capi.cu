@@ -2,6 +2,8 @@
 // See include/pigp.h for the contract and the reference interfaces each entry point replaces.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -12,6 +14,27 @@ namespace pigp {
 static thread_local std::string t_error;
 void set_error(const std::string& msg) { t_error = msg; }
 std::atomic<long long> g_launches{0};
+
+bool g_prof_on = false;
+struct ProfRec { int cls; cudaEvent_t e0, e1; double flops; int m, n, k, mode; };
+static int g_note[4] = {0, 0, 0, 0};
+void prof_note(int m, int n, int k, int mode) { g_note[0] = m; g_note[1] = n; g_note[2] = k; g_note[3] = mode; }
+static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;
+void prof_push(int cls, cudaStream_t st, bool begin, double flops) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (begin) {
+        ProfRec r{cls, nullptr, nullptr, flops, g_note[0], g_note[1], g_note[2], g_note[3]};
+        g_note[0] = g_note[1] = g_note[2] = g_note[3] = 0;
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, st);
+        g_prof.push_back(r);
+    } else {
+        for (size_t i = g_prof.size(); i-- > 0;)
+            if (g_prof[i].cls == cls) { cudaEventRecord(g_prof[i].e1, st); break; }
+    }
+}
 
 static void add_tiles(std::vector<AsmTile>& out, int64_t r0, int64_t r1, int64_t c0, int64_t c1, int desc, int flags) {
     for (int64_t r = r0; r < r1; r += ASM_TR) {
@@ -134,6 +157,40 @@ extern "C" {
 int pigp_abi_version(void) { return PIGP_ABI_VERSION; }
 const char* pigp_last_error(void) { return t_error.c_str(); }
 int64_t pigp_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int pigp_profile_start(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.clear();
+    g_prof_on = true;
+    return PIGP_OK;
+}
+
+int pigp_profile_stop(double* ms_out, int64_t* launches_out, double* flops_out) {
+    g_prof_on = false;
+    PIGP_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int c = 0; c < PIGP_PROF_CLASSES; ++c) {
+        if (ms_out) ms_out[c] = 0.0;
+        if (launches_out) launches_out[c] = 0;
+        if (flops_out) flops_out[c] = 0.0;
+    }
+    FILE* dump = nullptr;
+    if (const char* path = getenv("PIGP_PROF_DUMP")) dump = fopen(path, "w");
+    if (dump) fprintf(dump, "class,ms,flops,m,n,k,mode\n");
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        if (dump) fprintf(dump, "%d,%.6f,%.0f,%d,%d,%d,%d\n", r.cls, ms, r.flops, r.m, r.n, r.k, r.mode);
+        if (ms_out) ms_out[r.cls] += ms;
+        if (launches_out) launches_out[r.cls] += 1;
+        if (flops_out) flops_out[r.cls] += r.flops;
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    if (dump) fclose(dump);
+    g_prof.clear();
+    return PIGP_OK;
+}
 
 int pigp_set_device(int device) {
     PIGP_CUDA(cudaSetDevice(device));
@@ -344,9 +401,12 @@ static int factor(pigp_solver* s, const double* theta, const double* y, double e
     PIGP_TRY(launch_assemble(p, p->d_tiles_lower, p->n_tiles_lower, theta, eps, 1, s->A, ld, st));
     PIGP_TRY(launch_pad(s->A, ld, s->n, s->n, s->npad, s->npad, 1, 1, st));
     const int yblock = (s->yrow < s->npad) ? 1 : TILE;
-    k_set_yrow<<<(unsigned)std::min<int64_t>((yblock * s->npad + 255) / 256, 1184), 256, 0, st>>>(
-        s->A, ld, s->n, s->npad, s->yrow, yblock, y, 1e300);
-    count_launch();
+    {
+        ProfScope prof(PROF_MISC, st);
+        k_set_yrow<<<(unsigned)std::min<int64_t>((yblock * s->npad + 255) / 256, 1184), 256, 0, st>>>(
+            s->A, ld, s->n, s->npad, s->yrow, yblock, y, 1e300);
+        count_launch();
+    }
     PIGP_CUDA(cudaGetLastError());
     return potrf_lower(s->A, ld, s->npad, (s->mrow0 - s->npad) + extra_rows, s->invd, info, st);
 }

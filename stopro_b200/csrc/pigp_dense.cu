@@ -181,6 +181,21 @@ int launch_gemm(const GemmDesc& g, cudaStream_t st) {
     }
     auto run = [&](const GemmDesc& d, int64_t ntiles) {
         const dim3 grid((unsigned)ntiles), block(GEMM_THREADS);
+        double flops = 0.0;
+        if (g_prof_on) {  // flops executed at tile granularity
+            const int kt = d.K / BK, per = BM / BK;
+            const int dnt = d.N / BN;
+            const int dmt = d.lower_only ? dnt : d.M / BM;  // the lower_only launch covers the square part only
+            for (int tm = 0; tm < dmt; ++tm) {
+                const int ncols = d.lower_only ? tm + 1 : dnt;
+                int kb = 0, ke = kt;
+                if (d.kmode == 1) kb = tm * per;
+                else if (d.kmode == 2) ke = std::min(kt, (tm + 1) * per);
+                flops += 2.0 * BM * BN * BK * (double)std::max(0, ke - kb) * ncols;
+            }
+            prof_note(d.lower_only ? d.N : d.M, d.N, d.K, d.kmode * 10 + d.lower_only);
+        }
+        ProfScope prof(PROF_GEMM, st, flops);
         if (d.a_kcontig && d.b_kcontig) k_gemm<true, true><<<grid, block, GEMM_SMEM, st>>>(d);
         else if (d.a_kcontig) k_gemm<true, false><<<grid, block, GEMM_SMEM, st>>>(d);
         else if (d.b_kcontig) k_gemm<false, true><<<grid, block, GEMM_SMEM, st>>>(d);
@@ -290,6 +305,7 @@ static int launch_potf2(double* A, int64_t ld, double* invd, int32_t* info, int 
         PIGP_CUDA(cudaFuncSetAttribute(k_potf2, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM));
         attr_set = true;
     }
+    ProfScope prof(PROF_POTF2, st);
     k_potf2<<<1, 256, POTF2_SMEM, st>>>(A, ld, invd, info, base);
     count_launch();
     PIGP_CUDA(cudaGetLastError());
@@ -381,8 +397,11 @@ int potri_lower(const double* L, int64_t ld, int64_t n, const double* invd, doub
         set_error("pigp potri: n must be a multiple of 128 and ld even");
         return PIGP_EINVAL;
     }
-    k_place_diag<<<(unsigned)(n / TILE), 256, 0, st>>>(W, ld, invd);
-    count_launch();
+    {
+        ProfScope prof(PROF_MISC, st);
+        k_place_diag<<<(unsigned)(n / TILE), 256, 0, st>>>(W, ld, invd);
+        count_launch();
+    }
     PIGP_CUDA(cudaGetLastError());
     PIGP_TRY(trtri_rec(L, W, ld, n, st));
     // X (lower) = W^T W :  X_ij = sum_{k >= i} W[k][i] W[k][j]
@@ -427,6 +446,7 @@ __global__ void __launch_bounds__(1024) k_logdet_quad(const double* A, int64_t l
 }
 
 int launch_logdet_quad(const double* A, int64_t ld, int64_t n, const double* v, double* out2, cudaStream_t st) {
+    ProfScope prof(PROF_MISC, st);
     k_logdet_quad<<<1, 1024, 0, st>>>(A, ld, n, v, out2);
     count_launch();
     PIGP_CUDA(cudaGetLastError());
@@ -469,6 +489,7 @@ __global__ void __launch_bounds__(256) k_sum_chunks(const double* part, int64_t 
 
 int launch_trmv_lower_t(const double* W, int64_t ld, int64_t n, const double* x, double* y, double* part, cudaStream_t st) {
     const int n_chunks = (int)((n + TRMV_CHUNK - 1) / TRMV_CHUNK);
+    ProfScope prof(PROF_MISC, st);
     k_trmv_lower_t<<<dim3((unsigned)((n + 127) / 128), (unsigned)n_chunks), 256, 0, st>>>(W, ld, n, x, part);
     k_sum_chunks<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, n, n_chunks, y);
     count_launch(2);
@@ -499,6 +520,7 @@ __global__ void __launch_bounds__(256) k_gemv(const double* A, int64_t ld, int64
 
 int launch_gemv(const double* A, int64_t ld, int64_t m, int64_t n, const double* x, double* y, cudaStream_t st) {
     if (m <= 0) return PIGP_OK;
+    ProfScope prof(PROF_MISC, st);
     k_gemv<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(A, ld, m, n, x, y);
     count_launch();
     PIGP_CUDA(cudaGetLastError());

@@ -34,6 +34,17 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
         if (_rc != PIGP_OK) return _rc; \
     } while (0)
 
+// ---- optional per-class event timing (pigp_profile_start / _stop)
+enum { PROF_ASSEMBLE = 0, PROF_GEMM = 1, PROF_POTF2 = 2, PROF_GRAD = 3, PROF_MISC = 4 };
+extern bool g_prof_on;
+void prof_push(int cls, cudaStream_t st, bool begin, double flops);
+void prof_note(int m, int n, int k, int mode);  // shape of the next record (written to $PIGP_PROF_DUMP by pigp_profile_stop)
+struct ProfScope {
+    int cls; cudaStream_t st; bool on;
+    ProfScope(int c, cudaStream_t s, double flops = 0.0) : cls(c), st(s), on(g_prof_on) { if (on) prof_push(cls, st, true, flops); }
+    ~ProfScope() { if (on) prof_push(cls, st, false, 0.0); }
+};
+
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 // One rectangle of the output matrix, evaluated by one CTA of the assembly / gradient kernels.
