@@ -201,19 +201,19 @@ class GPmodel:
     def __getattr__(self, name):
         # K<a><b>(r, rp, theta): cov(a(r), b(rp)), e.g. Kuxfx, Kfxdiv, Kdifuxdifux, Kpdifp (gp_2D_stokes_independent.py:22-246)
         if name.startswith("K") and not name.startswith("Kernel") and "_obs" in self.__dict__:
-            rest = name[1:]
-            for a in sorted(self._obs, key=len, reverse=True):
-                if rest.startswith(a) and rest[len(a):] in self._obs:
-                    oa, ob = self._obs[a], self._obs[rest[len(a):]]
+            try:
+                oa, ob = operators.parse_block_name(name, self._obs)
+            except KeyError:
+                raise AttributeError(name) from None
 
-                    def block(r, rp, theta, _oa=oa, _ob=ob):
-                        plan = Plan(self.dim, self.product_form, self._fields, [_oa], [r], [_ob], [rp], lbox=self.lbox)
-                        try:
-                            return plan.assemble_host(np.asarray(theta, dtype=np.float64)[:self.n_kernel_theta])
-                        finally:
-                            plan.close()
+            def block(r, rp, theta):
+                plan = Plan(self.dim, self.product_form, self._fields, [oa], [r], [ob], [rp], lbox=self.lbox)
+                try:
+                    return plan.assemble_host(np.asarray(theta, dtype=np.float64)[:self.n_kernel_theta])
+                finally:
+                    plan.close()
 
-                    return block
+            return block
         raise AttributeError(name)
 
     def close(self):

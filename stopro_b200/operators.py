@@ -110,3 +110,15 @@ def describe(desc, dim):
         t = desc.terms[k]
         out.append((t.group, t.coef, tuple(t.order[i] for i in range(dim))))
     return out, bool(desc.shift_first), bool(desc.shift_second)
+
+
+def parse_block_name(name, obs):
+    """'Kuxfx' -> (obs['ux'], obs['fx']): the naming scheme of the reference's block library (K<a><b>)."""
+    if not name.startswith("K"):
+        raise KeyError(name)
+    rest = name[1:]
+    for a in sorted(obs, key=len, reverse=True):
+        if rest.startswith(a) and rest[len(a):] in obs:
+            return obs[a], obs[rest[len(a):]]
+    raise KeyError(name)
+
