@@ -12,7 +12,7 @@ TILE = 128
 LAYOUT_FULL, LAYOUT_LOWER = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpigp.so")
+LIB_PATH = os.environ.get("PIGP_LIB") or os.path.join(_HERE, "libpigp.so")  # PIGP_LIB: alternate build (kernel tuning only)
 
 
 class Term(C.Structure):

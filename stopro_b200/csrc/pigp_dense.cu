@@ -18,11 +18,22 @@
 namespace pigp {
 
 // ----------------------------------------------------------------------------------------------- GEMM
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 3, GEMM_THREADS = 256;
-constexpr int LDS_K = BK + 4;   // k-contiguous operand tile  [128][20]  (row stride = 4 mod 16 doubles: conflict-free fragment loads)
-constexpr int LDS_M = BM + 4;   // m-contiguous operand tile  [16][132]
-constexpr int OPD = BM * LDS_K; // doubles per operand per stage (2560 >= 16*132)
+constexpr int BM = 128, BN = 128, GEMM_THREADS = 256;
+#ifndef PIGP_GEMM_BK
+#define PIGP_GEMM_BK 16
+#endif
+#ifndef PIGP_GEMM_STAGES
+#define PIGP_GEMM_STAGES 4
+#endif
+constexpr int BK = PIGP_GEMM_BK, STAGES = PIGP_GEMM_STAGES;
+// Shared-memory operand tiles.  Fragments are fetched with 16-byte loads (two k values, or two rows, per load):
+//   k-contiguous operand  [128][BK + 8]  row stride = 8 mod 16 doubles  -> the 8 lanes of a quarter warp hit 8 distinct 16-byte slots
+//   m-contiguous operand  [BK][130]      row stride = 2 mod 8 doubles   -> same property for the (k, row-pair) pattern
+constexpr int LDS_K = BK + 8;
+constexpr int LDS_M = BM + 2;
+constexpr int OPD = (BM * LDS_K > BK * LDS_M) ? BM * LDS_K : BK * LDS_M;  // doubles per operand per stage
 constexpr int GEMM_SMEM = STAGES * 2 * OPD * (int)sizeof(double);
+constexpr int SUPER = 12;  // tiles are issued in 12 x 12 super-tiles so that the ~148 resident CTAs share operand panels in L2
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -41,19 +52,40 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 
 template <bool KC>
 __device__ __forceinline__ void load_operand(double* sm, const double* G, int64_t ld, int64_t row0, int64_t k0, int tid) {
-    if (KC) {  // X(row, k) = G[row*ld + k]: 128 rows x 16 doubles, 8 16-byte chunks per row
+    constexpr int PER_THREAD = BM * BK / 2 / GEMM_THREADS;
+    if (KC) {  // X(row, k) = G[row*ld + k]: 128 rows x BK doubles, BK/2 16-byte chunks per row
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < PER_THREAD; ++i) {
             const int c = tid + i * GEMM_THREADS;
-            const int r = c >> 3, ch = c & 7;
+            const int r = c / (BK / 2), ch = c % (BK / 2);
             cp_async16(sm + r * LDS_K + ch * 2, G + (row0 + r) * ld + k0 + ch * 2);
         }
-    } else {   // X(row, k) = G[k*ld + row]: 16 k-rows x 128 doubles, 64 chunks per k-row
+    } else {   // X(row, k) = G[k*ld + row]: BK k-rows x 128 doubles, 64 chunks per k-row
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < PER_THREAD; ++i) {
             const int c = tid + i * GEMM_THREADS;
             const int kr = c >> 6, ch = c & 63;
             cp_async16(sm + kr * LDS_M + ch * 2, G + (k0 + kr) * ld + row0 + ch * 2);
+        }
+    }
+}
+
+// Fragments of one 8-wide k group for NT 8-row sub-tiles starting at row `base` of the operand tile.
+// frag[i].x feeds the MMA over k = {0,2,4,6} + k8 (lane tig supplies k8 + 2 tig), frag[i].y the one over {1,3,5,7} + k8.
+// k-contiguous: sub-tile i = rows base + 8 i + gid.  m-contiguous: sub-tiles (2p, 2p+1) = rows base + 16 p + 2 gid + {0, 1}.
+template <bool KC, int NT>
+__device__ __forceinline__ void load_frags(double2* frag, const double* sm, int base, int k8, int gid, int tig) {
+    if (KC) {
+#pragma unroll
+        for (int i = 0; i < NT; ++i)
+            frag[i] = *reinterpret_cast<const double2*>(sm + (base + 8 * i + gid) * LDS_K + k8 + 2 * tig);
+    } else {
+#pragma unroll
+        for (int p = 0; p < NT / 2; ++p) {
+            const double2 e = *reinterpret_cast<const double2*>(sm + (k8 + 2 * tig) * LDS_M + base + 16 * p + 2 * gid);
+            const double2 o = *reinterpret_cast<const double2*>(sm + (k8 + 2 * tig + 1) * LDS_M + base + 16 * p + 2 * gid);
+            frag[2 * p] = make_double2(e.x, o.x);
+            frag[2 * p + 1] = make_double2(e.y, o.y);
         }
     }
 }
@@ -65,17 +97,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm(GemmDesc g) {
     const int gid = lane >> 2, tig = lane & 3;
     const int wm = warp & 1, wn = warp >> 1;  // 2 x 4 warps, warp tile 64 x 32
 
+    const int nt = g.N / BN;
+    const int mt = g.lower_only ? nt : g.M / BM;  // a lower_only launch covers the square part only
     int tm, tn;
-    if (g.lower_only) {
-        const int idx = blockIdx.x;
-        tm = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
-        while ((tm + 1) * (tm + 2) / 2 <= idx) ++tm;
-        while (tm * (tm + 1) / 2 > idx) --tm;
-        tn = idx - tm * (tm + 1) / 2;
-    } else {
-        const int mt = g.M / BM;
-        tm = blockIdx.x % mt;
-        tn = blockIdx.x / mt;
+    {
+        const int sidx = blockIdx.x / (SUPER * SUPER), local = blockIdx.x % (SUPER * SUPER);
+        int sm_, sn_;
+        if (g.lower_only) {  // super-tiles in lower-triangular order
+            sm_ = (int)((sqrt(8.0 * sidx + 1.0) - 1.0) * 0.5);
+            while ((sm_ + 1) * (sm_ + 2) / 2 <= sidx) ++sm_;
+            while (sm_ * (sm_ + 1) / 2 > sidx) --sm_;
+            sn_ = sidx - sm_ * (sm_ + 1) / 2;
+        } else {
+            const int smt = (mt + SUPER - 1) / SUPER;
+            sm_ = sidx % smt;
+            sn_ = sidx / smt;
+        }
+        tm = sm_ * SUPER + local % SUPER;
+        tn = sn_ * SUPER + local / SUPER;
+        if (tm >= mt || tn >= nt || (g.lower_only && tn > tm)) return;
     }
     const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
     int kt_begin = 0, kt_end = g.K / BK;
@@ -112,61 +152,64 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm(GemmDesc g) {
         const double* sA = smem + (it % STAGES) * 2 * OPD;
         const double* sB = sA + OPD;
 #pragma unroll
-        for (int kk = 0; kk < BK / 4; ++kk) {
-            double af[8], bf[4];
-#pragma unroll
-            for (int mi = 0; mi < 8; ++mi) {
-                const int r = wm * 64 + mi * 8 + gid, k = kk * 4 + tig;
-                af[mi] = AKC ? sA[r * LDS_K + k] : sA[k * LDS_M + r];
-            }
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-                const int r = wn * 32 + ni * 8 + gid, k = kk * 4 + tig;
-                bf[ni] = BKC ? sB[r * LDS_K + k] : sB[k * LDS_M + r];
-            }
+        for (int k8 = 0; k8 < BK; k8 += 8) {
+            double2 af[8], bf[4];
+            load_frags<AKC, 8>(af, sA, wm * 64, k8, gid, tig);
+            load_frags<BKC, 4>(bf, sB, wn * 32, k8, gid, tig);
 #pragma unroll
             for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+                for (int ni = 0; ni < 4; ++ni) {
+                    dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi].x, bf[ni].x);
+                    dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi].y, bf[ni].y);
+                }
         }
     }
     cp_async_wait<0>();
 
+    // epilogue.  Row of (sub-tile mi, lane group gid): 8 mi + gid (k-contiguous A) or 16 (mi/2) + 2 gid + (mi & 1).
+    // Columns: k-contiguous B: sub-tile ni holds columns 8 ni + 2 tig + {0,1}; m-contiguous B: the pair (2q, 2q+1) holds
+    // the four columns 16 q + 4 tig + {0,1,2,3} = {acc[2q][0], acc[2q+1][0], acc[2q][1], acc[2q+1][1]}.
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi) {
-        const int64_t r = m0 + wm * 64 + mi * 8 + gid;
+        const int lr = AKC ? (8 * mi + gid) : (16 * (mi >> 1) + 2 * gid + (mi & 1));
+        double* crow = g.C + (m0 + wm * 64 + lr) * g.ldc + n0 + wn * 32;
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            const int64_t c = n0 + wn * 32 + ni * 8 + tig * 2;
-            double2* p = reinterpret_cast<double2*>(g.C + r * g.ldc + c);
-            double2 o;
-            o.x = g.alpha * acc[mi][ni][0];
-            o.y = g.alpha * acc[mi][ni][1];
-            if (g.beta != 0.0) {
-                const double2 old = *p;
-                o.x = fma(g.beta, old.x, o.x);
-                o.y = fma(g.beta, old.y, o.y);
+        for (int q = 0; q < 2; ++q) {
+            double v[4];
+            int c0, c1;
+            if (BKC) {
+                v[0] = acc[mi][2 * q][0]; v[1] = acc[mi][2 * q][1]; v[2] = acc[mi][2 * q + 1][0]; v[3] = acc[mi][2 * q + 1][1];
+                c0 = 16 * q + 2 * tig;
+                c1 = c0 + 8;
+            } else {
+                v[0] = acc[mi][2 * q][0]; v[1] = acc[mi][2 * q + 1][0]; v[2] = acc[mi][2 * q][1]; v[3] = acc[mi][2 * q + 1][1];
+                c0 = 16 * q + 4 * tig;
+                c1 = c0 + 2;
             }
-            *p = o;
+            double2* p0 = reinterpret_cast<double2*>(crow + c0);
+            double2* p1 = reinterpret_cast<double2*>(crow + c1);
+            double2 o0 = make_double2(g.alpha * v[0], g.alpha * v[1]);
+            double2 o1 = make_double2(g.alpha * v[2], g.alpha * v[3]);
+            if (g.beta != 0.0) {
+                const double2 a0 = *p0, a1 = *p1;
+                o0.x = fma(g.beta, a0.x, o0.x); o0.y = fma(g.beta, a0.y, o0.y);
+                o1.x = fma(g.beta, a1.x, o1.x); o1.y = fma(g.beta, a1.y, o1.y);
+            }
+            *p0 = o0;
+            *p1 = o1;
         }
     }
 }
 
 int launch_gemm(const GemmDesc& g, cudaStream_t st) {
     if (g.M <= 0 || g.N <= 0) return PIGP_OK;
-    if (g.M % BM || g.N % BN || g.K % BK || g.K <= 0) {
-        set_error("pigp gemm: M, N must be multiples of 128 and K of 16");
+    if (g.M % BM || g.N % BN || g.K % 128 || g.K <= 0) {
+        set_error("pigp gemm: M, N and K must be multiples of 128");
         return PIGP_EINVAL;
     }
     const int mt = g.M / BM, nt = g.N / BN;
-    int64_t tiles;
-    if (g.lower_only) {
-        // tiles (tm, tn <= tm); rows beyond the square part (tm >= nt) have all nt column tiles
-        if (mt < nt) { set_error("pigp gemm: lower_only needs M >= N"); return PIGP_EINVAL; }
-        tiles = (int64_t)nt * (nt + 1) / 2;
-    } else {
-        tiles = (int64_t)mt * nt;
-    }
+    if (g.lower_only && mt < nt) { set_error("pigp gemm: lower_only needs M >= N"); return PIGP_EINVAL; }
     static bool attr_done[64] = {};
     int dev = 0;
     PIGP_CUDA(cudaGetDevice(&dev));
@@ -179,13 +222,14 @@ int launch_gemm(const GemmDesc& g, cudaStream_t st) {
         PIGP_CUDA(set_attr(k_gemm<false, false>));
         attr_set = true;
     }
-    auto run = [&](const GemmDesc& d, int64_t ntiles) {
-        const dim3 grid((unsigned)ntiles), block(GEMM_THREADS);
+    auto run = [&](const GemmDesc& d) {
+        const int dmt = d.lower_only ? d.N / BN : d.M / BM, dnt = d.N / BN;  // a lower_only launch covers the square part
+        const int smt = (dmt + SUPER - 1) / SUPER, snt = (dnt + SUPER - 1) / SUPER;
+        const int64_t supers = d.lower_only ? (int64_t)smt * (smt + 1) / 2 : (int64_t)smt * snt;
+        const dim3 grid((unsigned)(supers * SUPER * SUPER)), block(GEMM_THREADS);
         double flops = 0.0;
         if (g_prof_on) {  // flops executed at tile granularity
             const int kt = d.K / BK, per = BM / BK;
-            const int dnt = d.N / BN;
-            const int dmt = d.lower_only ? dnt : d.M / BM;  // the lower_only launch covers the square part only
             for (int tm = 0; tm < dmt; ++tm) {
                 const int ncols = d.lower_only ? tm + 1 : dnt;
                 int kb = 0, ke = kt;
@@ -202,7 +246,7 @@ int launch_gemm(const GemmDesc& g, cudaStream_t st) {
         else k_gemm<false, false><<<grid, block, GEMM_SMEM, st>>>(d);
         count_launch();
     };
-    run(g, tiles);
+    run(g);
     if (g.lower_only && mt > nt) {
         // rectangular remainder below the square part: rows [N, M)
         GemmDesc r = g;
@@ -211,88 +255,177 @@ int launch_gemm(const GemmDesc& g, cudaStream_t st) {
         r.A = g.a_kcontig ? g.A + (int64_t)g.N * g.lda : g.A + g.N;
         r.C = g.C + (int64_t)g.N * g.ldc;
         if (g.kmode != 0) { set_error("pigp gemm: kmode with rectangular lower_only is unsupported"); return PIGP_EINVAL; }
-        run(r, (int64_t)(r.M / BM) * nt);
+        run(r);
     }
     PIGP_CUDA(cudaGetLastError());
     return PIGP_OK;
 }
 
 // ----------------------------------------------------------------------------------------------- POTF2 (128 x 128)
+// One CTA (8 warps) factors a 128 x 128 diagonal tile held in shared memory and inverts the factor in place.
+// Blocked with 32 x 32 blocks so that only 4 x 32 column steps are sequential:
+//   per block column kb: warp 0 factors the 32 x 32 diagonal block in registers (lane = row, columns exchanged by
+//   shuffles) and inverts it; all warps then form the panel  L_ik = A_ik inv(L_kk)^T  and the trailing update
+//   A_ij -= L_ik L_jk^T  as 8 x 32 strips of FP64 MMAs (DMMA) out of shared memory.
+//   inverse: the two 64 x 64 diagonal halves from their 32-blocks, then W21 = -W22 (L21 W11); the (zero) upper-right
+//   64 x 64 quadrant of the tile is the scratch for L21 W11.
 constexpr int PT = 128;
-constexpr int PLD = PT + 1;  // odd row stride: column walks are conflict-free
-constexpr int POTF2_SMEM = PT * PLD * (int)sizeof(double);
+constexpr int PLD = PT + 4;   // 132 = 4 mod 16: conflict-free DMMA fragment loads in both orientations
+constexpr int SLD = 36;       // 32 x 32 scratch blocks, same residue
+constexpr int N_SCRATCH = 6;  // inv(L_kk) x 4, two temporaries
+constexpr int POTF2_SMEM = (PT * PLD + N_SCRATCH * 32 * SLD) * (int)sizeof(double);
 
-// Factor the lower triangle of the 128 x 128 tile at A in place (upper part of the tile is set to zero) and write
+// C(8 x 32 strip) = (accumulate ? C : 0) + alpha * sum_k A(row, k) * Bop(col, k);  Bop(col,k) = B_KN ? B[k][col] : B[col][k].
+// Pointers are pre-offset to the strip / operand origin.  n_tiles (1..4) of the four 8 x 8 column tiles are stored.
+template <bool B_KN>
+__device__ __forceinline__ void strip_mma(double* C, int ldc, const double* A, int lda, const double* B, int ldb, int K,
+                                          double alpha, bool accumulate, int n_tiles, int lane) {
+    const int gid = lane >> 2, tig = lane & 3;
+    double acc[4][2];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        if (accumulate && t < n_tiles) {
+            const double2 c = *reinterpret_cast<const double2*>(C + gid * ldc + t * 8 + tig * 2);
+            acc[t][0] = c.x;
+            acc[t][1] = c.y;
+        } else {
+            acc[t][0] = acc[t][1] = 0.0;
+        }
+    }
+    for (int k4 = 0; k4 < K; k4 += 4) {
+        const double a = alpha * A[gid * lda + k4 + tig];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const double b = B_KN ? B[(k4 + tig) * ldb + t * 8 + gid] : B[(t * 8 + gid) * ldb + k4 + tig];
+            dmma(acc[t][0], acc[t][1], a, b);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+        if (t < n_tiles) *reinterpret_cast<double2*>(C + gid * ldc + t * 8 + tig * 2) = make_double2(acc[t][0], acc[t][1]);
+}
+
+// Warp-level Cholesky + inverse of the 32 x 32 block at D (row stride ld): lane i owns row i.
+// L overwrites the lower triangle of D (zeros above), inv(L) goes to Winv (row stride SLD, zeros above).
+__device__ __forceinline__ void warp_potrf32(double* D, int ld, double* Winv, int32_t* info, int base, int lane) {
+    double a[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? D[lane * ld + c] : 0.0;
+    double my_rdiag = 0.0;  // 1 / L[lane][lane]
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const double d = __shfl_sync(0xffffffffu, a[j], j);
+        if (lane == 0 && !(d > 0.0) && info) atomicCAS(info, 0, base + j + 1);
+        const double rinv = rsqrt(d);  // NaN for d < 0, like the reference's jnp.linalg.cholesky
+        const double aj = (lane > j) ? a[j] * rinv : ((lane == j) ? d * rinv : 0.0);
+        a[j] = aj;
+        if (lane == j) my_rdiag = rinv;
+#pragma unroll
+        for (int k = j + 1; k < 32; ++k) {
+            const double lk = __shfl_sync(0xffffffffu, aj, k);  // L[k][j]
+            a[k] = fma(-aj, lk, a[k]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) D[lane * ld + c] = (c <= lane) ? a[c] : 0.0;
+    // inverse: lane j owns column j of W;  w[i] = (delta_ij - sum_{k<i} L[i][k] w[k]) / L[i][i]
+    double w[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) {
+            const double lik = __shfl_sync(0xffffffffu, a[k], i);  // L[i][k] from the lane that owns row i
+            if (k & 1) s1 = fma(lik, w[k], s1);
+            else s0 = fma(lik, w[k], s0);
+        }
+        const double rd = __shfl_sync(0xffffffffu, my_rdiag, i);
+        const double rhs = (lane == i) ? 1.0 : 0.0;
+        w[i] = (lane <= i) ? (rhs - (s0 + s1)) * rd : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) Winv[i * SLD + lane] = w[i];
+}
+
+// Factor the lower triangle of the 128 x 128 tile at A in place (the upper part of the tile is set to zero) and write
 // inv(L) (lower, zeros above) to invd[128*128].  Non-positive pivot -> *info = base + column + 1 (first one wins)
 // and NaNs propagate, which is what jnp.linalg.cholesky gives the reference.
 __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double* invd, int32_t* info, int base) {
     extern __shared__ __align__(16) double sm[];
-    __shared__ double s_part[2][PT];
-    const int tid = threadIdx.x;
+    double* scratch = sm + PT * PLD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int e = tid; e < PT * PT; e += 256) {
         const int i = e >> 7, j = e & 127;
         sm[i * PLD + j] = (j <= i) ? A[(int64_t)i * ld + j] : 0.0;
     }
-    const int row = tid & 127, half = tid >> 7;
-    for (int j = 0; j < PT; ++j) {
+    __syncthreads();
+    for (int kb = 0; kb < 4; ++kb) {
+        const int o = 32 * kb;
+        double* invk = scratch + kb * 32 * SLD;
+        if (warp == 0) warp_potrf32(sm + o * PLD + o, PLD, invk, info, base + o, lane);
         __syncthreads();
-        const double d = sm[j * PLD + j];
-        if (tid == 0 && !(d > 0.0) && info) atomicCAS(info, 0, base + j + 1);
-        const double rinv = 1.0 / sqrt(d);
-        __syncthreads();
-        // scale column j
-        if (half == 0) {
-            if (row > j) sm[row * PLD + j] *= rinv;
-            else if (row == j) sm[j * PLD + j] = d * rinv;
+        const int r_lo = o + 32;
+        const int n_strips = (PT - r_lo) / 8;
+        // panel: rows below the block, L_ik = A_ik inv(L_kk)^T, in place (a strip is read entirely before it is written)
+        for (int st = warp; st < n_strips; st += 8) {
+            double* X = sm + (r_lo + st * 8) * PLD + o;
+            strip_mma<false>(X, PLD, X, PLD, invk, SLD, 32, 1.0, false, 4, lane);
         }
         __syncthreads();
-        // trailing update: row `row`, columns k in (j, row], interleaved over the two halves
-        if (row > j) {
-            const double lij = sm[row * PLD + j];
-            double* mine = sm + row * PLD;
-            int k = j + 1 + half;
-            for (; k + 6 <= row; k += 8) {  // four independent updates per trip: loads first, stores last
-                const double l0 = sm[k * PLD + j], l1 = sm[(k + 2) * PLD + j], l2 = sm[(k + 4) * PLD + j], l3 = sm[(k + 6) * PLD + j];
-                const double c0 = mine[k], c1 = mine[k + 2], c2 = mine[k + 4], c3 = mine[k + 6];
-                mine[k] = fma(-lij, l0, c0);
-                mine[k + 2] = fma(-lij, l1, c1);
-                mine[k + 4] = fma(-lij, l2, c2);
-                mine[k + 6] = fma(-lij, l3, c3);
+        // trailing update (lower): tasks = (8-row strip, 32-column group at or left of it)
+        int task = 0;
+        for (int st = 0; st < n_strips; ++st) {
+            const int n_groups = st / 4 + 1;
+            for (int cg = 0; cg < n_groups; ++cg, ++task) {
+                if ((task & 7) != warp) continue;
+                const int r0 = r_lo + st * 8, c0 = r_lo + cg * 32;
+                const int n_tiles = min(4, (r0 - c0) / 8 + 1);  // tiles at or left of the diagonal tile
+                strip_mma<false>(sm + r0 * PLD + c0, PLD, sm + r0 * PLD + o, PLD, sm + c0 * PLD + o, PLD, 32, -1.0, true,
+                                 n_tiles, lane);
             }
-            for (; k <= row; k += 2) mine[k] = fma(-lij, sm[k * PLD + j], mine[k]);
         }
+        __syncthreads();
+    }
+    for (int e = tid; e < PT * PT; e += 256) {
+        const int i = e >> 7, j = e & 127;
+        A[(int64_t)i * ld + j] = (j <= i) ? sm[i * PLD + j] : 0.0;
+    }
+    // ---- inverse.  Step 1: off-diagonal 32-blocks of the two 64 x 64 halves, W_ba = -inv(L_b) (L_ba inv(L_a)).
+    {
+        const int half = warp >> 2, w4 = warp & 3;         // warps 0-3: blocks (1,0); warps 4-7: blocks (3,2)
+        const int ra = 64 * half, rb = ra + 32;
+        const double* inva = scratch + (2 * half) * 32 * SLD;
+        const double* invb = scratch + (2 * half + 1) * 32 * SLD;
+        double* tmp = scratch + (4 + half) * 32 * SLD;
+        double* Lba = sm + rb * PLD + ra;
+        strip_mma<true>(tmp + w4 * 8 * SLD, SLD, Lba + w4 * 8 * PLD, PLD, inva, SLD, 32, 1.0, false, 4, lane);
+        __syncthreads();
+        strip_mma<true>(Lba + w4 * 8 * PLD, PLD, invb + w4 * 8 * SLD, SLD, tmp, SLD, 32, -1.0, false, 4, lane);
+    }
+    __syncthreads();
+    // Step 2: diagonal 32-blocks <- inv(L_kk) (full blocks, zeros above the diagonal)
+    for (int e = tid; e < 4 * 32 * 32; e += 256) {
+        const int kb = e >> 10, i = (e >> 5) & 31, j = e & 31;
+        sm[(32 * kb + i) * PLD + 32 * kb + j] = scratch[kb * 32 * SLD + i * SLD + j];
+    }
+    __syncthreads();
+    // Step 3: T = L21 W11 into the upper-right quadrant; 16 tasks (8 strips x 2 column groups)
+    for (int task = warp; task < 16; task += 8) {
+        const int st = task >> 1, cg = task & 1;
+        strip_mma<true>(sm + (st * 8) * PLD + 64 + cg * 32, PLD, sm + (64 + st * 8) * PLD, PLD, sm + cg * 32, PLD, 64, 1.0,
+                        false, 4, lane);
+    }
+    __syncthreads();
+    // Step 4: W21 = -W22 T
+    for (int task = warp; task < 16; task += 8) {
+        const int st = task >> 1, cg = task & 1;
+        strip_mma<true>(sm + (64 + st * 8) * PLD + cg * 32, PLD, sm + (64 + st * 8) * PLD + 64, PLD, sm + 64 + cg * 32, PLD, 64,
+                        -1.0, false, 4, lane);
     }
     __syncthreads();
     for (int e = tid; e < PT * PT; e += 256) {
         const int i = e >> 7, j = e & 127;
-        A[(int64_t)i * ld + j] = sm[i * PLD + j];
-    }
-    // in-place inverse, row by row: W[i][j] = (delta_ij - sum_{k=j}^{i-1} L[i][k] W[k][j]) / L[i][i]
-    // thread (col = row, half): half 0 takes even offsets of k, half 1 odd offsets
-    const int col = row;
-    for (int i = 0; i < PT; ++i) {
-        __syncthreads();
-        double s0 = 0.0, s1 = 0.0;
-        if (col < i) {
-            int k = col + half;
-            for (; k + 2 < i; k += 4) {
-                s0 = fma(sm[i * PLD + k], sm[k * PLD + col], s0);
-                s1 = fma(sm[i * PLD + k + 2], sm[(k + 2) * PLD + col], s1);
-            }
-            for (; k < i; k += 2) s0 = fma(sm[i * PLD + k], sm[k * PLD + col], s0);
-        }
-        s_part[half][col] = s0 + s1;
-        const double dii = sm[i * PLD + i];
-        __syncthreads();
-        if (half == 0 && col <= i) {
-            const double rhs = (col == i) ? 1.0 : 0.0;
-            sm[i * PLD + col] = (rhs - (s_part[0][col] + s_part[1][col])) / dii;
-        }
-    }
-    __syncthreads();
-    for (int e = tid; e < PT * PT; e += 256) {
-        const int i = e >> 7, j = e & 127;
-        invd[e] = sm[i * PLD + j];
+        invd[e] = (j <= i) ? sm[i * PLD + j] : 0.0;
     }
 }
 

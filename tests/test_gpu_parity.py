@@ -107,7 +107,9 @@ def test_prediction(cuda_device, name):
     mu, cov = gp.predictingFunction_all(th, *args)
     mu_ref, cov_ref = ref.predictingFunction_all(th, *args)
     scale_mu = max(np.max(np.abs(m)) for m in mu_ref)
-    scale_cov = max(np.max(np.abs(c)) for c in cov_ref)
+    # the posterior covariance K_aa - V^T V is a difference of O(|K_aa|) terms: errors are judged on that scale
+    thk, _ = ref.split_hyp_and_noise(th)
+    scale_cov = max(np.max(np.abs(ref.testK_all(thk, ref._pts(cfg["r_test"])))), max(np.max(np.abs(c)) for c in cov_ref))
     for a, b in zip(mu, mu_ref):
         assert np.max(np.abs(a - b)) <= tol * scale_mu
     for a, b in zip(cov, cov_ref):
