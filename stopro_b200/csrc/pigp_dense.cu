@@ -12,13 +12,14 @@
 // * k_potf2: one CTA factors a 128 x 128 diagonal tile in shared memory and inverts the factor in place.
 // * Host drivers: recursive right-looking Cholesky (all flops in k_gemm), TRTRI + LAUUM for K^-1.
 #include <algorithm>
+#include <cstdlib>
 
 #include "pigp_internal.cuh"
 
 namespace pigp {
 
 // ----------------------------------------------------------------------------------------------- GEMM
-constexpr int BM = 128, BN = 128, GEMM_THREADS = 256;
+constexpr int BM = 128;
 #ifndef PIGP_GEMM_BK
 #define PIGP_GEMM_BK 16
 #endif
@@ -30,9 +31,9 @@ constexpr int BK = PIGP_GEMM_BK, STAGES = PIGP_GEMM_STAGES;
 //   k-contiguous operand  [128][BK + 8]  row stride = 8 mod 16 doubles  -> the 8 lanes of a quarter warp hit 8 distinct 16-byte slots
 //   m-contiguous operand  [BK][130]      row stride = 2 mod 8 doubles   -> same property for the (k, row-pair) pattern
 constexpr int LDS_K = BK + 8;
-constexpr int LDS_M = BM + 2;
-constexpr int OPD = (BM * LDS_K > BK * LDS_M) ? BM * LDS_K : BK * LDS_M;  // doubles per operand per stage
-constexpr int GEMM_SMEM = STAGES * 2 * OPD * (int)sizeof(double);
+__host__ __device__ constexpr int lds_m(int rows) { return rows + 2; }
+__host__ __device__ constexpr int opd(int rows) { return (rows * LDS_K > BK * lds_m(rows)) ? rows * LDS_K : BK * lds_m(rows); }  // doubles per operand tile
+__host__ __device__ constexpr int gemm_smem(int bn, int stages) { return stages * (opd(BM) + opd(bn)) * (int)sizeof(double); }
 constexpr int SUPER = 12;  // tiles are issued in 12 x 12 super-tiles so that the ~148 resident CTAs share operand panels in L2
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -50,22 +51,22 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-template <bool KC>
+template <bool KC, int ROWS, int THREADS>
 __device__ __forceinline__ void load_operand(double* sm, const double* G, int64_t ld, int64_t row0, int64_t k0, int tid) {
-    constexpr int PER_THREAD = BM * BK / 2 / GEMM_THREADS;
-    if (KC) {  // X(row, k) = G[row*ld + k]: 128 rows x BK doubles, BK/2 16-byte chunks per row
+    constexpr int PER_THREAD = ROWS * BK / 2 / THREADS;
+    if (KC) {  // X(row, k) = G[row*ld + k]: ROWS rows x BK doubles, BK/2 16-byte chunks per row
 #pragma unroll
         for (int i = 0; i < PER_THREAD; ++i) {
-            const int c = tid + i * GEMM_THREADS;
+            const int c = tid + i * THREADS;
             const int r = c / (BK / 2), ch = c % (BK / 2);
             cp_async16(sm + r * LDS_K + ch * 2, G + (row0 + r) * ld + k0 + ch * 2);
         }
-    } else {   // X(row, k) = G[k*ld + row]: BK k-rows x 128 doubles, 64 chunks per k-row
+    } else {   // X(row, k) = G[k*ld + row]: BK k-rows x ROWS doubles, ROWS/2 chunks per k-row
 #pragma unroll
         for (int i = 0; i < PER_THREAD; ++i) {
-            const int c = tid + i * GEMM_THREADS;
-            const int kr = c >> 6, ch = c & 63;
-            cp_async16(sm + kr * LDS_M + ch * 2, G + (k0 + kr) * ld + row0 + ch * 2);
+            const int c = tid + i * THREADS;
+            const int kr = c / (ROWS / 2), ch = c % (ROWS / 2);
+            cp_async16(sm + kr * lds_m(ROWS) + ch * 2, G + (k0 + kr) * ld + row0 + ch * 2);
         }
     }
 }
@@ -73,7 +74,7 @@ __device__ __forceinline__ void load_operand(double* sm, const double* G, int64_
 // Fragments of one 8-wide k group for NT 8-row sub-tiles starting at row `base` of the operand tile.
 // frag[i].x feeds the MMA over k = {0,2,4,6} + k8 (lane tig supplies k8 + 2 tig), frag[i].y the one over {1,3,5,7} + k8.
 // k-contiguous: sub-tile i = rows base + 8 i + gid.  m-contiguous: sub-tiles (2p, 2p+1) = rows base + 16 p + 2 gid + {0, 1}.
-template <bool KC, int NT>
+template <bool KC, int NT, int ROWS>
 __device__ __forceinline__ void load_frags(double2* frag, const double* sm, int base, int k8, int gid, int tig) {
     if (KC) {
 #pragma unroll
@@ -82,26 +83,31 @@ __device__ __forceinline__ void load_frags(double2* frag, const double* sm, int 
     } else {
 #pragma unroll
         for (int p = 0; p < NT / 2; ++p) {
-            const double2 e = *reinterpret_cast<const double2*>(sm + (k8 + 2 * tig) * LDS_M + base + 16 * p + 2 * gid);
-            const double2 o = *reinterpret_cast<const double2*>(sm + (k8 + 2 * tig + 1) * LDS_M + base + 16 * p + 2 * gid);
+            const double2 e = *reinterpret_cast<const double2*>(sm + (k8 + 2 * tig) * lds_m(ROWS) + base + 16 * p + 2 * gid);
+            const double2 o = *reinterpret_cast<const double2*>(sm + (k8 + 2 * tig + 1) * lds_m(ROWS) + base + 16 * p + 2 * gid);
             frag[2 * p] = make_double2(e.x, o.x);
             frag[2 * p + 1] = make_double2(e.y, o.y);
         }
     }
 }
 
-template <bool AKC, bool BKC>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm(GemmDesc g) {
+// BN_ = 128: 8 warps, one CTA per SM.  BN_ = 64: 4 warps, two CTAs per SM (independent barriers: while one CTA waits at its
+// barrier or on shared-memory loads, the other keeps the FP64 tensor pipe busy).
+template <bool AKC, bool BKC, int BN_, int STAGES_>
+__global__ void __launch_bounds__(BN_ * 2, 128 / BN_) k_gemm(GemmDesc g) {
+    constexpr int THREADS = BN_ * 2;
+    constexpr int OPA = opd(BM), OPB = opd(BN_), STG = OPA + OPB;
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
-    const int wm = warp & 1, wn = warp >> 1;  // 2 x 4 warps, warp tile 64 x 32
+    const int wm = warp & 1, wn = warp >> 1;  // 2 x (BN_/32) warps, warp tile 64 x 32
 
-    const int nt = g.N / BN;
-    const int mt = g.lower_only ? nt : g.M / BM;  // a lower_only launch covers the square part only
+    const int nt = g.N / BN_;
+    const int mt = g.lower_only ? g.N / BM : g.M / BM;  // a lower_only launch covers the square part only
     int tm, tn;
     {
-        const int sidx = blockIdx.x / (SUPER * SUPER), local = blockIdx.x % (SUPER * SUPER);
+        constexpr int SN = SUPER * (BM / BN_);  // column tiles per super-tile (super-tiles are square in elements)
+        const int sidx = blockIdx.x / (SUPER * SN), local = blockIdx.x % (SUPER * SN);
         int sm_, sn_;
         if (g.lower_only) {  // super-tiles in lower-triangular order
             sm_ = (int)((sqrt(8.0 * sidx + 1.0) - 1.0) * 0.5);
@@ -114,10 +120,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm(GemmDesc g) {
             sn_ = sidx / smt;
         }
         tm = sm_ * SUPER + local % SUPER;
-        tn = sn_ * SUPER + local / SUPER;
-        if (tm >= mt || tn >= nt || (g.lower_only && tn > tm)) return;
+        tn = sn_ * SN + local / SUPER;
+        if (tm >= mt || tn >= nt || (g.lower_only && (int64_t)tn * BN_ > (int64_t)tm * BM + (BM - BN_))) return;
     }
-    const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
+    const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN_;
     int kt_begin = 0, kt_end = g.K / BK;
     if (g.kmode == 1) kt_begin = tm * (BM / BK);
     else if (g.kmode == 2) kt_end = min(kt_end, (tm + 1) * (BM / BK));
@@ -130,39 +136,40 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm(GemmDesc g) {
 
     const int nk = kt_end - kt_begin;
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
+    for (int s = 0; s < STAGES_ - 1; ++s) {
         if (s < nk) {
-            load_operand<AKC>(smem + s * 2 * OPD, g.A, g.lda, m0, (int64_t)(kt_begin + s) * BK, tid);
-            load_operand<BKC>(smem + s * 2 * OPD + OPD, g.B, g.ldb, n0, (int64_t)(kt_begin + s) * BK, tid);
+            load_operand<AKC, BM, THREADS>(smem + s * STG, g.A, g.lda, m0, (int64_t)(kt_begin + s) * BK, tid);
+            load_operand<BKC, BN_, THREADS>(smem + s * STG + OPA, g.B, g.ldb, n0, (int64_t)(kt_begin + s) * BK, tid);
         }
         cp_async_commit();
     }
     for (int it = 0; it < nk; ++it) {
-        cp_async_wait<STAGES - 2>();
+        cp_async_wait<STAGES_ - 2>();
         __syncthreads();
         {
-            const int nx = it + STAGES - 1;
+            const int nx = it + STAGES_ - 1;
             if (nx < nk) {
-                const int s = nx % STAGES;
-                load_operand<AKC>(smem + s * 2 * OPD, g.A, g.lda, m0, (int64_t)(kt_begin + nx) * BK, tid);
-                load_operand<BKC>(smem + s * 2 * OPD + OPD, g.B, g.ldb, n0, (int64_t)(kt_begin + nx) * BK, tid);
+                const int s = nx % STAGES_;
+                load_operand<AKC, BM, THREADS>(smem + s * STG, g.A, g.lda, m0, (int64_t)(kt_begin + nx) * BK, tid);
+                load_operand<BKC, BN_, THREADS>(smem + s * STG + OPA, g.B, g.ldb, n0, (int64_t)(kt_begin + nx) * BK, tid);
             }
             cp_async_commit();
         }
-        const double* sA = smem + (it % STAGES) * 2 * OPD;
-        const double* sB = sA + OPD;
+        const double* sA = smem + (it % STAGES_) * STG;
+        const double* sB = sA + OPA;
 #pragma unroll
         for (int k8 = 0; k8 < BK; k8 += 8) {
             double2 af[8], bf[4];
-            load_frags<AKC, 8>(af, sA, wm * 64, k8, gid, tig);
-            load_frags<BKC, 4>(bf, sB, wn * 32, k8, gid, tig);
+            load_frags<AKC, 8, BM>(af, sA, wm * 64, k8, gid, tig);
+            load_frags<BKC, 4, BN_>(bf, sB, wn * 32, k8, gid, tig);
 #pragma unroll
             for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) {
-                    dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi].x, bf[ni].x);
-                    dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi].y, bf[ni].y);
-                }
+                for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi].x, bf[ni].x);
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi].y, bf[ni].y);
         }
     }
     cp_async_wait<0>();
@@ -202,52 +209,62 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm(GemmDesc g) {
     }
 }
 
-int launch_gemm(const GemmDesc& g, cudaStream_t st) {
-    if (g.M <= 0 || g.N <= 0) return PIGP_OK;
-    if (g.M % BM || g.N % BN || g.K % 128 || g.K <= 0) {
-        set_error("pigp gemm: M, N and K must be multiples of 128");
-        return PIGP_EINVAL;
-    }
-    const int mt = g.M / BM, nt = g.N / BN;
-    if (g.lower_only && mt < nt) { set_error("pigp gemm: lower_only needs M >= N"); return PIGP_EINVAL; }
+static int g_gemm_bn = 0;  // 0: read PIGP_GEMM_BN once (kernel tuning); 128 or 64
+
+template <int BN_, int STAGES_>
+static int launch_gemm_cfg(const GemmDesc& d, cudaStream_t st) {
+    constexpr int SMEM = gemm_smem(BN_, STAGES_);
     static bool attr_done[64] = {};
     int dev = 0;
     PIGP_CUDA(cudaGetDevice(&dev));
     bool& attr_set = attr_done[dev & 63];
-    auto set_attr = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM); };
+    auto set_attr = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); };
     if (!attr_set) {
-        PIGP_CUDA(set_attr(k_gemm<true, true>));
-        PIGP_CUDA(set_attr(k_gemm<true, false>));
-        PIGP_CUDA(set_attr(k_gemm<false, true>));
-        PIGP_CUDA(set_attr(k_gemm<false, false>));
+        PIGP_CUDA(set_attr(k_gemm<true, true, BN_, STAGES_>));
+        PIGP_CUDA(set_attr(k_gemm<true, false, BN_, STAGES_>));
+        PIGP_CUDA(set_attr(k_gemm<false, true, BN_, STAGES_>));
+        PIGP_CUDA(set_attr(k_gemm<false, false, BN_, STAGES_>));
         attr_set = true;
     }
-    auto run = [&](const GemmDesc& d) {
-        const int dmt = d.lower_only ? d.N / BN : d.M / BM, dnt = d.N / BN;  // a lower_only launch covers the square part
-        const int smt = (dmt + SUPER - 1) / SUPER, snt = (dnt + SUPER - 1) / SUPER;
-        const int64_t supers = d.lower_only ? (int64_t)smt * (smt + 1) / 2 : (int64_t)smt * snt;
-        const dim3 grid((unsigned)(supers * SUPER * SUPER)), block(GEMM_THREADS);
-        double flops = 0.0;
-        if (g_prof_on) {  // flops executed at tile granularity
-            const int kt = d.K / BK, per = BM / BK;
-            for (int tm = 0; tm < dmt; ++tm) {
-                const int ncols = d.lower_only ? tm + 1 : dnt;
-                int kb = 0, ke = kt;
-                if (d.kmode == 1) kb = tm * per;
-                else if (d.kmode == 2) ke = std::min(kt, (tm + 1) * per);
-                flops += 2.0 * BM * BN * BK * (double)std::max(0, ke - kb) * ncols;
-            }
-            prof_note(d.lower_only ? d.N : d.M, d.N, d.K, d.kmode * 10 + d.lower_only);
+    const int dmt = d.lower_only ? d.N / BM : d.M / BM, dnt_e = d.N / BM;  // in 128-element units
+    const int smt = (dmt + SUPER - 1) / SUPER, snt = (dnt_e + SUPER - 1) / SUPER;
+    const int64_t supers = d.lower_only ? (int64_t)smt * (smt + 1) / 2 : (int64_t)smt * snt;
+    const dim3 grid((unsigned)(supers * SUPER * SUPER * (BM / BN_))), block(BN_ * 2);
+    double flops = 0.0;
+    if (g_prof_on) {  // flops executed at 128-tile granularity
+        const int kt = d.K / BK, per = BM / BK;
+        for (int tm = 0; tm < dmt; ++tm) {
+            const int ncols = d.lower_only ? tm + 1 : dnt_e;
+            int kb = 0, ke = kt;
+            if (d.kmode == 1) kb = tm * per;
+            else if (d.kmode == 2) ke = std::min(kt, (tm + 1) * per);
+            flops += 2.0 * BM * BM * BK * (double)std::max(0, ke - kb) * ncols;
         }
-        ProfScope prof(PROF_GEMM, st, flops);
-        if (d.a_kcontig && d.b_kcontig) k_gemm<true, true><<<grid, block, GEMM_SMEM, st>>>(d);
-        else if (d.a_kcontig) k_gemm<true, false><<<grid, block, GEMM_SMEM, st>>>(d);
-        else if (d.b_kcontig) k_gemm<false, true><<<grid, block, GEMM_SMEM, st>>>(d);
-        else k_gemm<false, false><<<grid, block, GEMM_SMEM, st>>>(d);
-        count_launch();
-    };
-    run(g);
-    if (g.lower_only && mt > nt) {
+        prof_note(d.lower_only ? d.N : d.M, d.N, d.K, d.kmode * 10 + d.lower_only);
+    }
+    ProfScope prof(PROF_GEMM, st, flops);
+    if (d.a_kcontig && d.b_kcontig) k_gemm<true, true, BN_, STAGES_><<<grid, block, SMEM, st>>>(d);
+    else if (d.a_kcontig) k_gemm<true, false, BN_, STAGES_><<<grid, block, SMEM, st>>>(d);
+    else if (d.b_kcontig) k_gemm<false, true, BN_, STAGES_><<<grid, block, SMEM, st>>>(d);
+    else k_gemm<false, false, BN_, STAGES_><<<grid, block, SMEM, st>>>(d);
+    count_launch();
+    return PIGP_OK;
+}
+
+int launch_gemm(const GemmDesc& g, cudaStream_t st) {
+    if (g.M <= 0 || g.N <= 0) return PIGP_OK;
+    if (g.M % BM || g.N % BM || g.K % 128 || g.K <= 0) {
+        set_error("pigp gemm: M, N and K must be multiples of 128");
+        return PIGP_EINVAL;
+    }
+    if (g.lower_only && g.M < g.N) { set_error("pigp gemm: lower_only needs M >= N"); return PIGP_EINVAL; }
+    if (g_gemm_bn == 0) {
+        const char* e = getenv("PIGP_GEMM_BN");
+        g_gemm_bn = (e && atoi(e) == 128) ? 128 : 64;
+    }
+    auto run = [&](const GemmDesc& d) { return g_gemm_bn == 128 ? launch_gemm_cfg<128, 4>(d, st) : launch_gemm_cfg<64, 3>(d, st); };
+    PIGP_TRY(run(g));
+    if (g.lower_only && g.M > g.N) {
         // rectangular remainder below the square part: rows [N, M)
         GemmDesc r = g;
         r.lower_only = 0;
@@ -255,7 +272,7 @@ int launch_gemm(const GemmDesc& g, cudaStream_t st) {
         r.A = g.a_kcontig ? g.A + (int64_t)g.N * g.lda : g.A + g.N;
         r.C = g.C + (int64_t)g.N * g.ldc;
         if (g.kmode != 0) { set_error("pigp gemm: kmode with rectangular lower_only is unsupported"); return PIGP_EINVAL; }
-        run(r);
+        PIGP_TRY(run(r));
     }
     PIGP_CUDA(cudaGetLastError());
     return PIGP_OK;
