@@ -150,6 +150,28 @@ int pigp_dgemm(int M, int N, int K, double alpha, const double* A_dev, int64_t l
                const double* B_dev, int64_t ldb, int b_kcontig, double beta, double* C_dev, int64_t ldc,
                int lower_only, void* stream);
 
+/* --- multi-GPU evaluation (new; the reference is single device).  One pigp_dsolver per rank; 128-row tile t of K
+ * belongs to rank t mod world.  Ranks exchange data by stores into each other's slab over NVLink (P2P) and epoch flags;
+ * the slabs are made mutually visible either with CUDA IPC (one process per GPU: _ipc_handle on every rank, exchange
+ * the 64-byte handles with any host-side transport, pigp_ipc_open, _connect) or by passing raw pointers (several ranks
+ * in one process).  Every rank must issue the same sequence of pigp_dsolver_nll_grad calls.  All ranks receive the
+ * same NLL and (bitwise) the same gradient. */
+#define PIGP_IPC_HANDLE_BYTES 64
+typedef struct pigp_dsolver pigp_dsolver;
+int pigp_dsolver_create(pigp_plan* training_plan, int rank, int world, pigp_dsolver** out);
+void pigp_dsolver_destroy(pigp_dsolver* s);
+int pigp_dsolver_slab(const pigp_dsolver* s, void** ptr, int64_t* bytes);
+int pigp_dsolver_ipc_handle(const pigp_dsolver* s, void* handle64);
+int pigp_ipc_open(const void* handle64, void** ptr);
+int pigp_ipc_close(void* ptr);
+int pigp_dsolver_connect(pigp_dsolver* s, void* const* slabs /* world pointers; entry [rank] is ignored */);
+/* trainingFunction_all + d_trainingFunction_all (GP/gp.py:213-224, :412-488) over the sharded K.  grad_dev may be NULL
+ * (NLL only).  Asynchronous on `stream`. */
+int pigp_dsolver_nll_grad(pigp_dsolver* s, const double* theta_dev, const double* y_dev, double eps, double* nll_dev,
+                          double* grad_dev, int32_t* info_dev, void* stream);
+int pigp_dsolver_nll_grad_host(pigp_dsolver* s, const double* theta_host, const double* y_host, double eps, int want_grad,
+                               double* nll_host, double* grad_host, int32_t* info_host);
+
 /* Kernel launches issued by this library since load (all threads); for bench.py's gpu_launches. */
 int64_t pigp_launch_count(void);
 

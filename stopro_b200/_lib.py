@@ -10,6 +10,7 @@ MAX_TERMS = 8
 MAX_GROUPS = 4
 TILE = 128
 LAYOUT_FULL, LAYOUT_LOWER = 0, 1
+IPC_HANDLE_BYTES = 64
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PIGP_LIB") or os.path.join(_HERE, "libpigp.so")  # PIGP_LIB: alternate build (kernel tuning only)
@@ -65,6 +66,17 @@ _SIGNATURES = {
     "pigp_potri_lower": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pigp_dgemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64,
                              C.c_int, C.c_double, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "pigp_dsolver_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "pigp_dsolver_destroy": (None, [C.c_void_p]),
+    "pigp_dsolver_slab": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "pigp_dsolver_ipc_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pigp_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pigp_ipc_close": (C.c_int, [C.c_void_p]),
+    "pigp_dsolver_connect": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pigp_dsolver_nll_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]),
+    "pigp_dsolver_nll_grad_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]),
     "pigp_launch_count": (C.c_int64, []),
     "pigp_profile_start": (C.c_int, []),
     "pigp_profile_stop": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

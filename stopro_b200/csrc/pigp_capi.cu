@@ -47,6 +47,26 @@ static void add_tiles(std::vector<AsmTile>& out, int64_t r0, int64_t r1, int64_t
     }
 }
 
+void build_lower_tiles_owned(const pigp_plan* p, int rank, int world, std::vector<AsmTile>& out) {
+    const int nb = p->n_row_blocks;
+    for (int i = 0; i < nb; ++i)
+        for (int j = 0; j <= i; ++j) {
+            const pigp_block_desc& b = p->table[(size_t)j * nb + i];  // lower block (i, j) = transpose of table[j][i]
+            const int desc = b.n_terms > 0 ? j * nb + i : -1;
+            const int flags = (i == j) ? ASM_LOWER : ASM_SWAP;
+            const int64_t r1 = p->sec_row[i + 1], c0 = p->sec_row[j], c1 = p->sec_row[j + 1];
+            for (int64_t r = p->sec_row[i]; r < r1;) {
+                const int nr = (int)std::min<int64_t>(std::min<int64_t>(ASM_TR, r1 - r), TILE - r % TILE);
+                if ((int)((r / TILE) % world) == rank)
+                    for (int64_t c = c0; c < c1; c += ASM_TC) {
+                        if ((flags & ASM_LOWER) && r + nr - 1 < c) continue;
+                        out.push_back(AsmTile{(int32_t)r, (int32_t)c, nr, (int)std::min<int64_t>(ASM_TC, c1 - c), desc, flags});
+                    }
+                r += nr;
+            }
+        }
+}
+
 static int upload_tiles(const std::vector<AsmTile>& v, AsmTile** dev, int64_t* n) {
     *n = (int64_t)v.size();
     *dev = nullptr;
@@ -442,7 +462,7 @@ int pigp_nll_grad(pigp_solver* s, const double* theta_dev, const double* y_dev, 
     // K^-1 over the factor (the y row / padding rows only add a decoupled identity-like block)
     PIGP_TRY(potri_lower(s->A, s->npad, s->npad, s->invd, s->W, s->A, st));
     PIGP_TRY(launch_trmv_lower_t(s->W, s->npad, s->npad, s->v, s->alpha, s->trmv_part, st));
-    return launch_grad(s->plan, theta_dev, s->A, s->npad, s->alpha, s->partials, grad_dev, st);
+    return launch_grad(s->plan, s->plan->d_tiles_lower, s->plan->n_tiles_lower, theta_dev, s->A, s->npad, s->alpha, s->partials, grad_dev, st);
 }
 
 int pigp_nll_grad_host(pigp_solver* s, const double* theta_host, const double* pts_host, const double* y_host, double eps,

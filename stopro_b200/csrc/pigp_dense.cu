@@ -103,13 +103,13 @@ __global__ void __launch_bounds__(BN_ * 2, 128 / BN_) k_gemm(GemmDesc g) {
     const int wm = warp & 1, wn = warp >> 1;  // 2 x (BN_/32) warps, warp tile 64 x 32
 
     const int nt = g.N / BN_;
-    const int mt = g.lower_only ? g.N / BM : g.M / BM;  // a lower_only launch covers the square part only
+    const int mt = (g.lower_only && !g.gen) ? g.N / BM : g.M / BM;  // a plain lower_only launch covers the square part only
     int tm, tn;
     {
         constexpr int SN = SUPER * (BM / BN_);  // column tiles per super-tile (super-tiles are square in elements)
         const int sidx = blockIdx.x / (SUPER * SN), local = blockIdx.x % (SUPER * SN);
         int sm_, sn_;
-        if (g.lower_only) {  // super-tiles in lower-triangular order
+        if (g.lower_only && !g.gen) {  // super-tiles in lower-triangular order
             sm_ = (int)((sqrt(8.0 * sidx + 1.0) - 1.0) * 0.5);
             while ((sm_ + 1) * (sm_ + 2) / 2 <= sidx) ++sm_;
             while (sm_ * (sm_ + 1) / 2 > sidx) --sm_;
@@ -121,12 +121,15 @@ __global__ void __launch_bounds__(BN_ * 2, 128 / BN_) k_gemm(GemmDesc g) {
         }
         tm = sm_ * SUPER + local % SUPER;
         tn = sn_ * SN + local / SUPER;
-        if (tm >= mt || tn >= nt || (g.lower_only && (int64_t)tn * BN_ > (int64_t)tm * BM + (BM - BN_))) return;
+        if (tm >= mt || tn >= nt) return;
     }
-    const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN_;
+    const int gm = g.m_gt0 + tm * g.m_ts;  // global row tile (== tm for a plain GEMM)
+    if (g.lower_only && (int64_t)g.n_gt0 * BM + (int64_t)tn * BN_ > (int64_t)gm * BM + (BM - BN_)) return;
+    const int64_t m0 = (int64_t)tm * g.m_ts * BM, n0 = (int64_t)tn * BN_;
     int kt_begin = 0, kt_end = g.K / BK;
-    if (g.kmode == 1) kt_begin = tm * (BM / BK);
-    else if (g.kmode == 2) kt_end = min(kt_end, (tm + 1) * (BM / BK));
+    if (g.kmode == 1) kt_begin = max(0, gm - g.k_gt0) * (BM / BK);
+    else if (g.kmode == 2) kt_end = min(kt_end, (gm - g.k_gt0 + 1) * (BM / BK));
+    if (kt_end <= kt_begin && g.beta == 1.0) return;  // nothing to add
 
     double acc[8][4][2];
 #pragma unroll
@@ -205,6 +208,14 @@ __global__ void __launch_bounds__(BN_ * 2, 128 / BN_) k_gemm(GemmDesc g) {
             }
             *p0 = o0;
             *p1 = o1;
+            if (g.npeers > 0 && gm < g.push_gm_end) {
+                const int64_t off = (crow - g.C) + c0, d1 = c1 - c0;
+                for (int p = 0; p < g.npeers; ++p) {
+                    double* q = g.Cpeer[p] + off;
+                    *reinterpret_cast<double2*>(q) = o0;
+                    *reinterpret_cast<double2*>(q + d1) = o1;
+                }
+            }
         }
     }
 }
@@ -226,21 +237,23 @@ static int launch_gemm_cfg(const GemmDesc& d, cudaStream_t st) {
         PIGP_CUDA(set_attr(k_gemm<false, false, BN_, STAGES_>));
         attr_set = true;
     }
-    const int dmt = d.lower_only ? d.N / BM : d.M / BM, dnt_e = d.N / BM;  // in 128-element units
+    const bool tri = d.lower_only && !d.gen;
+    const int dmt = tri ? d.N / BM : d.M / BM, dnt_e = d.N / BM;  // in 128-element units
     const int smt = (dmt + SUPER - 1) / SUPER, snt = (dnt_e + SUPER - 1) / SUPER;
-    const int64_t supers = d.lower_only ? (int64_t)smt * (smt + 1) / 2 : (int64_t)smt * snt;
+    const int64_t supers = tri ? (int64_t)smt * (smt + 1) / 2 : (int64_t)smt * snt;
     const dim3 grid((unsigned)(supers * SUPER * SUPER * (BM / BN_))), block(BN_ * 2);
     double flops = 0.0;
     if (g_prof_on) {  // flops executed at 128-tile granularity
         const int kt = d.K / BK, per = BM / BK;
         for (int tm = 0; tm < dmt; ++tm) {
-            const int ncols = d.lower_only ? tm + 1 : dnt_e;
+            const int gm = d.m_gt0 + tm * d.m_ts;
+            const int ncols = d.lower_only ? std::max(0, std::min(dnt_e, gm - d.n_gt0 + 1)) : dnt_e;
             int kb = 0, ke = kt;
-            if (d.kmode == 1) kb = tm * per;
-            else if (d.kmode == 2) ke = std::min(kt, (tm + 1) * per);
+            if (d.kmode == 1) kb = std::max(0, gm - d.k_gt0) * per;
+            else if (d.kmode == 2) ke = std::min(kt, (gm - d.k_gt0 + 1) * per);
             flops += 2.0 * BM * BM * BK * (double)std::max(0, ke - kb) * ncols;
         }
-        prof_note(d.lower_only ? d.N : d.M, d.N, d.K, d.kmode * 10 + d.lower_only);
+        prof_note(tri ? d.N : d.M, d.N, d.K, d.kmode * 10 + d.lower_only);
     }
     ProfScope prof(PROF_GEMM, st, flops);
     if (d.a_kcontig && d.b_kcontig) k_gemm<true, true, BN_, STAGES_><<<grid, block, SMEM, st>>>(d);
@@ -251,20 +264,24 @@ static int launch_gemm_cfg(const GemmDesc& d, cudaStream_t st) {
     return PIGP_OK;
 }
 
-int launch_gemm(const GemmDesc& g, cudaStream_t st) {
+int launch_gemm(const GemmDesc& g_in, cudaStream_t st) {
+    GemmDesc g = g_in;
     if (g.M <= 0 || g.N <= 0) return PIGP_OK;
     if (g.M % BM || g.N % BM || g.K % 128 || g.K <= 0) {
         set_error("pigp gemm: M, N and K must be multiples of 128");
         return PIGP_EINVAL;
     }
-    if (g.lower_only && g.M < g.N) { set_error("pigp gemm: lower_only needs M >= N"); return PIGP_EINVAL; }
+    if (g.m_ts == 0) g.m_ts = 1;
+    if (g.lower_only && !g.gen && g.M < g.N) { set_error("pigp gemm: lower_only needs M >= N"); return PIGP_EINVAL; }
     if (g_gemm_bn == 0) {
         const char* e = getenv("PIGP_GEMM_BN");
         g_gemm_bn = (e && atoi(e) == 128) ? 128 : 64;
     }
-    auto run = [&](const GemmDesc& d) { return g_gemm_bn == 128 ? launch_gemm_cfg<128, 4>(d, st) : launch_gemm_cfg<64, 3>(d, st); };
+    auto run = [&](const GemmDesc& d) {
+        return (g_gemm_bn == 128 || d.force_bn128) ? launch_gemm_cfg<128, 4>(d, st) : launch_gemm_cfg<64, 3>(d, st);
+    };
     PIGP_TRY(run(g));
-    if (g.lower_only && g.M > g.N) {
+    if (g.lower_only && !g.gen && g.M > g.N) {
         // rectangular remainder below the square part: rows [N, M)
         GemmDesc r = g;
         r.lower_only = 0;
@@ -367,7 +384,7 @@ __device__ __forceinline__ void warp_potrf32(double* D, int ld, double* Winv, in
 // Factor the lower triangle of the 128 x 128 tile at A in place (the upper part of the tile is set to zero) and write
 // inv(L) (lower, zeros above) to invd[128*128].  Non-positive pivot -> *info = base + column + 1 (first one wins)
 // and NaNs propagate, which is what jnp.linalg.cholesky gives the reference.
-__global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double* invd, int32_t* info, int base) {
+__global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double* invd, int32_t* info, int base, PeerTiles peers) {
     extern __shared__ __align__(16) double sm[];
     double* scratch = sm + PT * PLD;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -405,7 +422,9 @@ __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double*
     }
     for (int e = tid; e < PT * PT; e += 256) {
         const int i = e >> 7, j = e & 127;
-        A[(int64_t)i * ld + j] = (j <= i) ? sm[i * PLD + j] : 0.0;
+        const double v = (j <= i) ? sm[i * PLD + j] : 0.0;
+        A[(int64_t)i * ld + j] = v;
+        for (int p = 0; p < peers.n; ++p) peers.a[p][(int64_t)i * ld + j] = v;
     }
     // ---- inverse.  Step 1: off-diagonal 32-blocks of the two 64 x 64 halves, W_ba = -inv(L_b) (L_ba inv(L_a)).
     {
@@ -442,11 +461,13 @@ __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double*
     __syncthreads();
     for (int e = tid; e < PT * PT; e += 256) {
         const int i = e >> 7, j = e & 127;
-        invd[e] = (j <= i) ? sm[i * PLD + j] : 0.0;
+        const double v = (j <= i) ? sm[i * PLD + j] : 0.0;
+        invd[e] = v;
+        for (int p = 0; p < peers.n; ++p) peers.invd[p][e] = v;
     }
 }
 
-static int launch_potf2(double* A, int64_t ld, double* invd, int32_t* info, int base, cudaStream_t st) {
+int launch_potf2(double* A, int64_t ld, double* invd, int32_t* info, int base, const PeerTiles& peers, cudaStream_t st) {
     static bool attr_done[64] = {};
     int dev = 0;
     PIGP_CUDA(cudaGetDevice(&dev));
@@ -456,7 +477,7 @@ static int launch_potf2(double* A, int64_t ld, double* invd, int32_t* info, int 
         attr_set = true;
     }
     ProfScope prof(PROF_POTF2, st);
-    k_potf2<<<1, 256, POTF2_SMEM, st>>>(A, ld, invd, info, base);
+    k_potf2<<<1, 256, POTF2_SMEM, st>>>(A, ld, invd, info, base, peers);
     count_launch();
     PIGP_CUDA(cudaGetLastError());
     return PIGP_OK;
@@ -466,7 +487,7 @@ static int launch_potf2(double* A, int64_t ld, double* invd, int32_t* info, int 
 static int chol_rec(double* A, int64_t ld, int64_t n, int64_t m_below, double* invd, int32_t* info, int base,
                     cudaStream_t st) {
     if (n == TILE) {
-        PIGP_TRY(launch_potf2(A, ld, invd, info, base, st));
+        PIGP_TRY(launch_potf2(A, ld, invd, info, base, PeerTiles{}, st));
         if (m_below > 0) {
             // B <- B * inv(L)^T, in place: every CTA reads its own 128 rows completely before writing them
             GemmDesc g{};
@@ -475,6 +496,7 @@ static int chol_rec(double* A, int64_t ld, int64_t n, int64_t m_below, double* i
             g.A = A + TILE * ld; g.lda = ld; g.a_kcontig = 1;
             g.B = invd; g.ldb = TILE; g.b_kcontig = 1;
             g.C = A + TILE * ld; g.ldc = ld;
+            g.force_bn128 = 1;
             PIGP_TRY(launch_gemm(g, st));
         }
         return PIGP_OK;

@@ -1,0 +1,593 @@
+// Multi-GPU evaluation of the PIGP path (K8): NLL + dK/dtheta trace gradient with K dealt block-cyclically over ranks.
+//
+// The reference has no distributed code at all; this is the sharded form of GP/gp.py:213-224 and
+// :412-488 that BASELINE.json's north star asks for.  One pigp_dsolver per rank (one process per GPU, or several
+// ranks in one process for tests).  Ownership: 128-row tile t of K belongs to rank t mod P.
+//
+// Data path = stores into peer memory over NVLink from inside the producing kernels + epoch flags; no library
+// collective:
+//   * every rank assembles its own row tiles of K (lower part) into a GLOBAL-layout buffer L (npad columns);
+//   * recursive right-looking Cholesky restricted to own row tiles.  k_potf2 of the tile owner stores L_kk and
+//     inv(L_kk) into every peer; the TRSM GEMM (own rows x inv(L_kk)^T) stores its result tiles into every peer from
+//     its epilogue, so L ends up replicated and every trailing update reads local memory only;
+//   * Y = L^-T (row tile j of Y = column tile j of L^-1) needs only L: own row tiles, no communication, then one bulk
+//     push of the finished rows to all peers;
+//   * K^-1 = Y Y^T on own row tiles, fused trace-gradient reduction on own tiles, P partial gradients exchanged by
+//     peer stores and summed in rank order (deterministic, identical on every rank);
+//   * log-det, |L^-1 y|^2 and alpha = K^-1 y are computed redundantly from the replicated L / Y; each rank carries its
+//     own y row tile (placed at the first tile index >= npad/128 that it owns) through the TRSMs.
+#include <algorithm>
+#include <cstring>
+
+#include "pigp_internal.cuh"
+
+namespace pigp {
+
+typedef unsigned long long u64;
+
+struct PeerFlags { int n; u64* f[7]; };
+
+__global__ void k_signal(PeerFlags pf, int idx, u64 val) {
+    if ((int)threadIdx.x < pf.n) {
+        __threadfence_system();
+        u64* p = pf.f[threadIdx.x] + idx;
+        asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(val) : "memory");
+    }
+}
+
+// thread t waits until flags[idx0 + t * stride] >= val (t == skip is not waited for).  Bounded: after ~4 s the error
+// flag is raised and the kernel returns, so a lost peer can never hang the device.
+__global__ void k_wait(const u64* flags, int idx0, int stride, int count, int skip, u64 val, int* err) {
+    const int t = threadIdx.x;
+    if (t >= count || t == skip) return;
+    const u64* p = flags + idx0 + (int64_t)t * stride;
+    u64 t0 = 0, now = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t0));
+    for (;;) {
+        u64 v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+        if (v >= val) break;
+        asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(now));
+        if (now - t0 > 4000000000ull) { atomicExch(err, 1); break; }
+        __nanosleep(100);
+    }
+}
+
+// rows [tile * 128, +128), columns [tile * 128, npad) of the own Y row tiles -> the same place in every peer
+struct PeerBufs { int n; double* p[7]; };
+__global__ void __launch_bounds__(256) k_push_rows(const double* Y, int64_t ld, int64_t npad, int first, int stride, PeerBufs pb) {
+    const int tile = first + (blockIdx.x >> 7) * stride;
+    const int64_t row = (int64_t)tile * 128 + (blockIdx.x & 127);
+    const int64_t c0 = (int64_t)tile * 128;
+    const double2* src = reinterpret_cast<const double2*>(Y + row * ld + c0);
+    const int64_t n2 = (npad - c0) >> 1;
+    for (int64_t i = threadIdx.x; i < n2; i += 256) {
+        const double2 v = src[i];
+        for (int p = 0; p < pb.n; ++p) reinterpret_cast<double2*>(pb.p[p] + row * ld + c0)[i] = v;
+    }
+}
+
+// diagonal tile c of Y <- inv(L_cc)^T (full tile: zeros below the diagonal)
+__global__ void __launch_bounds__(256) k_place_diag_t(double* Y, int64_t ld, const double* invd, int first, int stride) {
+    const int c = first + blockIdx.x * stride;
+    double* dst = Y + (int64_t)c * 128 * ld + (int64_t)c * 128;
+    const double* src = invd + (int64_t)c * 128 * 128;
+    __shared__ double sh[32][33];
+    for (int bt = 0; bt < 16; ++bt) {  // 32 x 32 sub-blocks
+        const int bi = bt >> 2, bj = bt & 3;
+        for (int e = threadIdx.x; e < 1024; e += 256) sh[e >> 5][e & 31] = src[(bi * 32 + (e >> 5)) * 128 + bj * 32 + (e & 31)];
+        __syncthreads();
+        for (int e = threadIdx.x; e < 1024; e += 256) dst[(int64_t)(bj * 32 + (e >> 5)) * ld + bi * 32 + (e & 31)] = sh[e & 31][e >> 5];
+        __syncthreads();
+    }
+}
+
+// alpha[j] = sum_{k >= tile(j) * 128} Y[j][k] v[k]   (one warp per row; Y upper triangular by tiles)
+__global__ void __launch_bounds__(256) k_gemv_upper(const double* Y, int64_t ld, int64_t npad, const double* v, double* alpha) {
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= npad) return;
+    const int lane = threadIdx.x & 31;
+    const double* a = Y + row * ld;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int64_t j = (row >> 7 << 7) + lane;
+    for (; j + 96 < npad; j += 128) {
+        s0 = fma(a[j], v[j], s0);
+        s1 = fma(a[j + 32], v[j + 32], s1);
+        s2 = fma(a[j + 64], v[j + 64], s2);
+        s3 = fma(a[j + 96], v[j + 96], s3);
+    }
+    for (; j < npad; j += 32) s0 = fma(a[j], v[j], s0);
+    double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) alpha[row] = s;
+}
+
+// own y tile: first row = [y, 0 ...], other rows zero
+__global__ void __launch_bounds__(256) k_set_ytile(double* tile, int64_t ld, int64_t n, int64_t npad, const double* y) {
+    const int64_t total = 128 * npad;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / npad, c = e % npad;
+        tile[r * ld + c] = (r == 0 && c < n) ? y[c] : 0.0;
+    }
+}
+
+__global__ void k_push_vec(const double* src, int len, int slot, double* local_slots, PeerBufs pb) {
+    const int i = threadIdx.x;
+    if (i >= len) return;
+    const double v = src[i];
+    local_slots[slot * MAX_THETA + i] = v;
+    for (int p = 0; p < pb.n; ++p) pb.p[p][slot * MAX_THETA + i] = v;
+}
+
+__global__ void k_sum_slots(const double* slots, int world, int len, double* out, const int32_t* info, const int* err) {
+    const int i = threadIdx.x;
+    if (i >= len) return;
+    double s = 0.0;
+    for (int r = 0; r < world; ++r) s += slots[r * MAX_THETA + i];  // rank order: same result on every rank
+    if ((info && *info != 0) || (err && *err != 0)) s = nan("");
+    out[i] = s;
+}
+
+__global__ void k_finish_nll_d(const double* out2, int64_t n, const int32_t* info, const int* err, double* nll) {
+    double v = 0.5 * out2[1] + out2[0] + 0.5 * (double)n * log(2.0 * 3.14159265358979323846);  // GP/gp.py:85-89
+    if ((info && *info != 0) || (err && *err != 0)) v = nan("");
+    *nll = v;
+}
+
+// info <- 1-based index of the first diagonal entry of the replicated factor that is not a positive number (0: none).
+// Every rank derives the same value from its copy of L (the owner's k_potf2 saw the pivot itself).
+__global__ void __launch_bounds__(1024) k_diag_info(const double* L, int64_t ld, int64_t n, int32_t* info) {
+    __shared__ int best;
+    if (threadIdx.x == 0) best = 0x7fffffff;
+    __syncthreads();
+    int mine = 0x7fffffff;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x)
+        if (!(L[i * ld + i] > 0.0)) { mine = (int)i + 1; break; }
+    if (mine != 0x7fffffff) atomicMin(&best, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) *info = (best == 0x7fffffff) ? 0 : best;
+}
+
+__global__ void k_copy_v(const double* row, int64_t npad, double* v) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < npad) v[i] = row[i];
+}
+
+}  // namespace pigp
+
+using namespace pigp;
+
+struct pigp_dsolver {
+    pigp_plan* plan = nullptr;
+    int rank = 0, world = 1;
+    int64_t n = 0, npad = 0, ld = 0;
+    int T = 0;    // row tiles of the padded matrix
+    int gy = 0;   // tile index of this rank's y tile (>= T, == rank mod world)
+    char* slab = nullptr;
+    size_t slab_bytes = 0;
+    double* L = nullptr;       // (T + world) * 128 rows x ld: K -> L (replicated) -> own rows of K^-1
+    double* Y = nullptr;       // npad x ld: L^-T, upper
+    double* invd = nullptr;    // T inverse diagonal tiles
+    double* gslots = nullptr;  // world x MAX_THETA partial gradients
+    u64* flags = nullptr;
+    int n_flags = 0;
+    char* peer_slab[8] = {};
+    bool connected = false;
+    u64 epoch = 0;
+    // private (not shared)
+    AsmTile* d_tiles = nullptr;
+    int64_t n_tiles = 0;
+    double *partials = nullptr, *gpart = nullptr, *out2 = nullptr, *v = nullptr, *alpha = nullptr;
+    int32_t* info = nullptr;
+    int* err = nullptr;
+    double *d_theta = nullptr, *d_y = nullptr, *d_res = nullptr, *h_res = nullptr;
+    cudaStream_t own_stream = nullptr;  // the _host entry point runs here (ranks sharing a process must not share a stream)
+
+    int f_diag(int k) const { return k; }
+    int f_panel(int k, int src) const { return T + k * world + src; }
+    int f_ydone(int src) const { return T + T * world + src; }
+    int f_grad(int src) const { return T + T * world + world + src; }
+    int f_bar(int src) const { return T + T * world + 2 * world + src; }
+    template <class P> P* peer(int p, P* local) const { return reinterpret_cast<P*>(peer_slab[p] + (reinterpret_cast<char*>(local) - slab)); }
+    // first own tile >= a
+    int first_own(int a) const { return a + ((rank - a) % world + world) % world; }
+    int count_own(int a, int b) const { const int f = first_own(a); return f < b ? (b - f + world - 1) / world : 0; }
+};
+
+namespace {
+
+struct Ctx {
+    pigp_dsolver* s;
+    cudaStream_t st;
+    PeerFlags pf;
+    int npeers;
+    int others[7];
+};
+
+Ctx make_ctx(pigp_dsolver* s, cudaStream_t st) {
+    Ctx c{};
+    c.s = s; c.st = st;
+    int k = 0;
+    for (int p = 0; p < s->world; ++p)
+        if (p != s->rank) { c.others[k] = p; c.pf.f[k] = s->peer(p, s->flags); ++k; }
+    c.pf.n = c.npeers = k;
+    return c;
+}
+
+int signal(const Ctx& c, int idx) {
+    if (c.npeers == 0) return PIGP_OK;
+    ProfScope prof(PROF_MISC, c.st);
+    k_signal<<<1, 32, 0, c.st>>>(c.pf, idx, c.s->epoch);
+    count_launch();
+    PIGP_CUDA(cudaGetLastError());
+    return PIGP_OK;
+}
+
+int wait_one(const Ctx& c, int idx) {
+    if (c.npeers == 0) return PIGP_OK;
+    ProfScope prof(PROF_MISC, c.st);
+    k_wait<<<1, 32, 0, c.st>>>(c.s->flags, idx, 0, 1, -1, c.s->epoch, c.s->err);
+    count_launch();
+    PIGP_CUDA(cudaGetLastError());
+    return PIGP_OK;
+}
+
+// flags[idx0 + src] for every src != rank
+int wait_all(const Ctx& c, int idx0) {
+    if (c.npeers == 0) return PIGP_OK;
+    ProfScope prof(PROF_MISC, c.st);
+    k_wait<<<1, 32, 0, c.st>>>(c.s->flags, idx0, 1, c.s->world, c.s->rank, c.s->epoch, c.s->err);
+    count_launch();
+    PIGP_CUDA(cudaGetLastError());
+    return PIGP_OK;
+}
+
+void set_push(const Ctx& c, GemmDesc& g, double* Cbase) {
+    g.npeers = c.npeers;
+    g.push_gm_end = c.s->T;
+    for (int k = 0; k < c.npeers; ++k) g.Cpeer[k] = c.s->peer(c.others[k], Cbase);
+}
+
+// ---- Cholesky over column tiles [c0, c0 + nt)
+int chol_leaf(const Ctx& c, int k) {
+    pigp_dsolver* s = c.s;
+    const int64_t ld = s->ld;
+    double* invk = s->invd + (int64_t)k * TILE * TILE;
+    if (k % s->world == s->rank) {
+        double* Akk = s->L + (int64_t)k * TILE * ld + (int64_t)k * TILE;
+        PeerTiles pt{};
+        pt.n = c.npeers;
+        for (int q = 0; q < c.npeers; ++q) { pt.a[q] = s->peer(c.others[q], Akk); pt.invd[q] = s->peer(c.others[q], invk); }
+        PIGP_TRY(launch_potf2(Akk, ld, invk, s->info, k * TILE, pt, c.st));
+        PIGP_TRY(signal(c, s->f_diag(k)));
+    } else {
+        PIGP_TRY(wait_one(c, s->f_diag(k)));
+    }
+    const int first = s->first_own(k + 1), cnt = s->count_own(k + 1, s->gy + 1);
+    if (cnt > 0) {
+        GemmDesc g{};
+        g.M = cnt * TILE; g.N = TILE; g.K = TILE;
+        g.alpha = 1.0; g.beta = 0.0;
+        double* Cb = s->L + (int64_t)first * TILE * ld + (int64_t)k * TILE;
+        g.A = Cb; g.lda = ld; g.a_kcontig = 1;
+        g.B = invk; g.ldb = TILE; g.b_kcontig = 1;
+        g.C = Cb; g.ldc = ld;
+        g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = k; g.k_gt0 = k;
+        g.force_bn128 = 1;  // in place
+        set_push(c, g, Cb);
+        PIGP_TRY(launch_gemm(g, c.st));
+    }
+    return signal(c, s->f_panel(k, s->rank));
+}
+
+int chol_rec(const Ctx& c, int c0, int nt) {
+    pigp_dsolver* s = c.s;
+    if (nt == 1) return chol_leaf(c, c0);
+    const int n1 = nt / 2, n2 = nt - n1;
+    PIGP_TRY(chol_rec(c, c0, n1));
+    PIGP_TRY(wait_all(c, s->f_panel(c0 + n1 - 1, 0)));
+    const int first = s->first_own(c0 + n1), cnt = s->count_own(c0 + n1, s->gy + 1);
+    if (cnt > 0) {
+        const int64_t ld = s->ld;
+        GemmDesc g{};
+        g.M = cnt * TILE; g.N = n2 * TILE; g.K = n1 * TILE;
+        g.alpha = -1.0; g.beta = 1.0;
+        g.A = s->L + (int64_t)first * TILE * ld + (int64_t)c0 * TILE; g.lda = ld; g.a_kcontig = 1;
+        g.B = s->L + (int64_t)(c0 + n1) * TILE * ld + (int64_t)c0 * TILE; g.ldb = ld; g.b_kcontig = 1;
+        g.C = s->L + (int64_t)first * TILE * ld + (int64_t)(c0 + n1) * TILE; g.ldc = ld;
+        g.lower_only = 1;
+        g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = c0 + n1; g.k_gt0 = c0;
+        PIGP_TRY(launch_gemm(g, c.st));
+    }
+    return chol_rec(c, c0 + n1, n2);
+}
+
+// ---- Y = L^-T on own row tiles, column tiles [c0, c0 + nt)
+int trtri_rec(const Ctx& c, int c0, int nt) {
+    pigp_dsolver* s = c.s;
+    const int64_t ld = s->ld;
+    if (nt == 1) {
+        const int first = s->first_own(0), cnt = s->count_own(0, c0);  // own rows strictly above the diagonal tile
+        if (cnt > 0) {
+            GemmDesc g{};
+            g.M = cnt * TILE; g.N = TILE; g.K = TILE;
+            g.alpha = 1.0; g.beta = 0.0;
+            double* Cb = s->Y + (int64_t)first * TILE * ld + (int64_t)c0 * TILE;
+            g.A = Cb; g.lda = ld; g.a_kcontig = 1;
+            g.B = s->invd + (int64_t)c0 * TILE * TILE; g.ldb = TILE; g.b_kcontig = 1;
+            g.C = Cb; g.ldc = ld;
+            g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = c0; g.k_gt0 = c0;
+            g.force_bn128 = 1;
+            PIGP_TRY(launch_gemm(g, c.st));
+        }
+        return PIGP_OK;
+    }
+    const int n1 = nt / 2, n2 = nt - n1;
+    PIGP_TRY(trtri_rec(c, c0, n1));
+    const int first = s->first_own(0), cnt = s->count_own(0, c0 + n1);
+    if (cnt > 0) {
+        // Y[j, J2] -= sum_{k in K1, k >= j} Y[j, k] L[J2, k]^T
+        GemmDesc g{};
+        g.M = cnt * TILE; g.N = n2 * TILE; g.K = n1 * TILE;
+        g.alpha = -1.0; g.beta = 1.0;
+        g.A = s->Y + (int64_t)first * TILE * ld + (int64_t)c0 * TILE; g.lda = ld; g.a_kcontig = 1;
+        g.B = s->L + (int64_t)(c0 + n1) * TILE * ld + (int64_t)c0 * TILE; g.ldb = ld; g.b_kcontig = 1;
+        g.C = s->Y + (int64_t)first * TILE * ld + (int64_t)(c0 + n1) * TILE; g.ldc = ld;
+        g.kmode = 1;
+        g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = c0 + n1; g.k_gt0 = c0;
+        PIGP_TRY(launch_gemm(g, c.st));
+    }
+    return trtri_rec(c, c0 + n1, n2);
+}
+
+}  // namespace
+
+extern "C" {
+
+void pigp_dsolver_destroy(pigp_dsolver* s) {
+    if (!s) return;
+    cudaFree(s->slab); cudaFree(s->d_tiles); cudaFree(s->partials); cudaFree(s->gpart); cudaFree(s->out2); cudaFree(s->v);
+    cudaFree(s->alpha); cudaFree(s->info); cudaFree(s->err); cudaFree(s->d_theta); cudaFree(s->d_y); cudaFree(s->d_res);
+    if (s->h_res) cudaFreeHost(s->h_res);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    delete s;
+}
+
+int pigp_dsolver_create(pigp_plan* plan, int rank, int world, pigp_dsolver** out) {
+    if (!plan || !out || !plan->symmetric || world < 1 || world > 8 || rank < 0 || rank >= world) {
+        set_error("pigp_dsolver_create: needs a symmetric training plan and 0 <= rank < world <= 8");
+        return PIGP_EINVAL;
+    }
+    *out = nullptr;
+    pigp_dsolver* s = new pigp_dsolver();
+    s->plan = plan; s->rank = rank; s->world = world;
+    s->n = plan->rows;
+    s->npad = round_up(s->n, TILE);
+    s->ld = s->npad;
+    s->T = (int)(s->npad / TILE);
+    s->gy = s->first_own(s->T);
+    s->n_flags = s->T + s->T * world + 3 * world;
+    const size_t l_bytes = sizeof(double) * (size_t)(s->T + world) * TILE * s->ld;
+    const size_t y_bytes = sizeof(double) * (size_t)s->npad * s->ld;
+    const size_t i_bytes = sizeof(double) * (size_t)s->T * TILE * TILE;
+    const size_t g_bytes = sizeof(double) * (size_t)world * MAX_THETA;
+    const size_t f_bytes = (sizeof(u64) * (size_t)s->n_flags + 255) / 256 * 256;
+    s->slab_bytes = l_bytes + y_bytes + i_bytes + ((g_bytes + 255) / 256 * 256) + f_bytes;
+    int rc = PIGP_OK;
+    auto cuda_ok = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && rc == PIGP_OK) { set_error(std::string(what) + ": " + cudaGetErrorString(e)); rc = PIGP_ECUDA; }
+    };
+    cuda_ok(cudaMalloc(&s->slab, s->slab_bytes), "cudaMalloc slab");
+    if (rc == PIGP_OK) {
+        char* p = s->slab;
+        s->L = reinterpret_cast<double*>(p); p += l_bytes;
+        s->Y = reinterpret_cast<double*>(p); p += y_bytes;
+        s->invd = reinterpret_cast<double*>(p); p += i_bytes;
+        s->gslots = reinterpret_cast<double*>(p); p += (g_bytes + 255) / 256 * 256;
+        s->flags = reinterpret_cast<u64*>(p);
+        cuda_ok(cudaMemset(s->flags, 0, f_bytes), "memset flags");
+        cuda_ok(cudaMemset(s->gslots, 0, g_bytes), "memset gslots");
+        s->peer_slab[rank] = s->slab;
+    }
+    std::vector<AsmTile> tiles;
+    build_lower_tiles_owned(plan, rank, world, tiles);
+    s->n_tiles = (int64_t)tiles.size();
+    if (rc == PIGP_OK && !tiles.empty()) {
+        cuda_ok(cudaMalloc(&s->d_tiles, tiles.size() * sizeof(AsmTile)), "cudaMalloc tiles");
+        if (rc == PIGP_OK) cuda_ok(cudaMemcpy(s->d_tiles, tiles.data(), tiles.size() * sizeof(AsmTile), cudaMemcpyHostToDevice), "copy tiles");
+    }
+    cuda_ok(cudaMalloc(&s->partials, sizeof(double) * std::max<int64_t>(s->n_tiles, 1) * MAX_THETA), "cudaMalloc partials");
+    cuda_ok(cudaMalloc(&s->gpart, sizeof(double) * MAX_THETA), "cudaMalloc gpart");
+    cuda_ok(cudaMalloc(&s->out2, sizeof(double) * 2), "cudaMalloc out2");
+    cuda_ok(cudaMalloc(&s->v, sizeof(double) * s->npad), "cudaMalloc v");
+    cuda_ok(cudaMalloc(&s->alpha, sizeof(double) * s->npad), "cudaMalloc alpha");
+    cuda_ok(cudaMalloc(&s->info, sizeof(int32_t)), "cudaMalloc info");
+    cuda_ok(cudaMalloc(&s->err, sizeof(int)), "cudaMalloc err");
+    if (rc == PIGP_OK) cuda_ok(cudaMemset(s->err, 0, sizeof(int)), "memset err");
+    cuda_ok(cudaMalloc(&s->d_theta, sizeof(double) * MAX_THETA), "cudaMalloc theta");
+    cuda_ok(cudaMalloc(&s->d_y, sizeof(double) * s->n), "cudaMalloc y");
+    cuda_ok(cudaMalloc(&s->d_res, sizeof(double) * (1 + MAX_THETA)), "cudaMalloc res");
+    cuda_ok(cudaMallocHost(&s->h_res, sizeof(double) * (4 + 2 * MAX_THETA) + sizeof(double) * s->n), "cudaMallocHost res");
+    cuda_ok(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (rc != PIGP_OK) { pigp_dsolver_destroy(s); return rc; }
+    s->connected = (world == 1);
+    *out = s;
+    return PIGP_OK;
+}
+
+int pigp_dsolver_slab(const pigp_dsolver* s, void** ptr, int64_t* bytes) {
+    if (!s) { set_error("pigp_dsolver_slab: null solver"); return PIGP_EINVAL; }
+    if (ptr) *ptr = s->slab;
+    if (bytes) *bytes = (int64_t)s->slab_bytes;
+    return PIGP_OK;
+}
+
+int pigp_dsolver_ipc_handle(const pigp_dsolver* s, void* handle64) {
+    if (!s || !handle64) { set_error("pigp_dsolver_ipc_handle: null argument"); return PIGP_EINVAL; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == PIGP_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    PIGP_CUDA(cudaIpcGetMemHandle(&h, s->slab));
+    std::memcpy(handle64, &h, sizeof(h));
+    return PIGP_OK;
+}
+
+int pigp_ipc_open(const void* handle64, void** ptr) {
+    if (!handle64 || !ptr) { set_error("pigp_ipc_open: null argument"); return PIGP_EINVAL; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, sizeof(h));
+    PIGP_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PIGP_OK;
+}
+
+int pigp_ipc_close(void* ptr) {
+    if (ptr) PIGP_CUDA(cudaIpcCloseMemHandle(ptr));
+    return PIGP_OK;
+}
+
+int pigp_dsolver_connect(pigp_dsolver* s, void* const* slabs) {
+    if (!s || !slabs) { set_error("pigp_dsolver_connect: null argument"); return PIGP_EINVAL; }
+    int me = 0;
+    PIGP_CUDA(cudaGetDevice(&me));
+    for (int p = 0; p < s->world; ++p) {
+        if (p == s->rank) continue;
+        if (!slabs[p]) { set_error("pigp_dsolver_connect: missing peer slab"); return PIGP_EINVAL; }
+        s->peer_slab[p] = static_cast<char*>(slabs[p]);
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, slabs[p]) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device != me) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);  // same-process peers on another device
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+                return PIGP_ECUDA;
+            }
+        }
+        cudaGetLastError();
+    }
+    s->connected = true;
+    return PIGP_OK;
+}
+
+int pigp_dsolver_nll_grad(pigp_dsolver* s, const double* theta_dev, const double* y_dev, double eps, double* nll_dev,
+                          double* grad_dev, int32_t* info_dev, void* stream) {
+    if (!s || !theta_dev || !y_dev || !nll_dev) { set_error("pigp_dsolver_nll_grad: null argument"); return PIGP_EINVAL; }
+    if (!s->connected) { set_error("pigp_dsolver_nll_grad: peers are not connected"); return PIGP_EINVAL; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const pigp_plan* p = s->plan;
+    const int64_t ld = s->ld;
+    s->epoch += 1;
+    Ctx c = make_ctx(s, st);
+    int32_t* info = s->info;
+    PIGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
+    // every peer has finished reading what the previous call left in this rank's buffers
+    PIGP_TRY(signal(c, s->f_bar(s->rank)));
+    PIGP_TRY(wait_all(c, s->f_bar(0)));
+    // own rows of K (lower, jitter added), identity padding (owner of the last tile), own y tile
+    PIGP_TRY(launch_assemble(p, s->d_tiles, s->n_tiles, theta_dev, eps, 1, s->L, ld, st));
+    if (s->n < s->npad && (s->T - 1) % s->world == s->rank)
+        PIGP_TRY(launch_pad(s->L, ld, s->n, s->n, s->npad, s->npad, 1, 1, st));
+    double* ytile = s->L + (int64_t)s->gy * TILE * ld;
+    {
+        ProfScope prof(PROF_MISC, st);
+        k_set_ytile<<<148, 256, 0, st>>>(ytile, ld, s->n, s->npad, y_dev);
+        count_launch();
+    }
+    PIGP_CUDA(cudaGetLastError());
+    PIGP_TRY(chol_rec(c, 0, s->T));
+    // every rank holds all of L now (the last panel flags of every peer were awaited inside chol_rec for all but the
+    // final leaf; the final diagonal tile arrives with its DIAG flag)
+    PIGP_TRY(launch_logdet_quad(s->L, ld, s->n, ytile, s->out2, st));
+    k_diag_info<<<1, 1024, 0, st>>>(s->L, ld, s->n, info);
+    count_launch();
+    k_finish_nll_d<<<1, 1, 0, st>>>(s->out2, s->n, info, s->err, nll_dev);
+    count_launch();
+    PIGP_CUDA(cudaGetLastError());
+    if (grad_dev) {
+        // Y = L^-T on own row tiles
+        const int first = s->first_own(0), cnt = s->count_own(0, s->T);
+        if (cnt > 0) {
+            PIGP_CUDA(cudaMemset2DAsync(s->Y + (int64_t)first * TILE * ld, sizeof(double) * TILE * ld * s->world, 0,
+                                        sizeof(double) * TILE * ld, cnt, st));
+            ProfScope prof(PROF_MISC, st);
+            k_place_diag_t<<<cnt, 256, 0, st>>>(s->Y, ld, s->invd, first, s->world);
+            count_launch();
+        }
+        PIGP_CUDA(cudaGetLastError());
+        PIGP_TRY(trtri_rec(c, 0, s->T));
+        if (c.npeers > 0) {
+            if (cnt > 0) {
+                PeerBufs pb{};
+                pb.n = c.npeers;
+                for (int q = 0; q < c.npeers; ++q) pb.p[q] = s->peer(c.others[q], s->Y);
+                ProfScope prof(PROF_MISC, st);
+                k_push_rows<<<cnt * TILE, 256, 0, st>>>(s->Y, ld, s->npad, first, s->world, pb);
+                count_launch();
+                PIGP_CUDA(cudaGetLastError());
+            }
+            PIGP_TRY(signal(c, s->f_ydone(s->rank)));
+            PIGP_TRY(wait_all(c, s->f_ydone(0)));
+        }
+        // alpha = K^-1 y = Y (L^-1 y), redundantly on every rank
+        {
+            ProfScope prof(PROF_MISC, st);
+            k_copy_v<<<(unsigned)((s->npad + 255) / 256), 256, 0, st>>>(ytile, s->npad, s->v);
+            k_gemv_upper<<<(unsigned)((s->npad + 7) / 8), 256, 0, st>>>(s->Y, ld, s->npad, s->v, s->alpha);
+            count_launch(2);
+        }
+        PIGP_CUDA(cudaGetLastError());
+        // own row tiles of K^-1 = Y Y^T (lower) over the own rows of L
+        if (cnt > 0) {
+            GemmDesc g{};
+            g.M = cnt * TILE; g.N = (int)s->npad; g.K = (int)s->npad;
+            g.alpha = 1.0; g.beta = 0.0;
+            g.A = s->Y + (int64_t)first * TILE * ld; g.lda = ld; g.a_kcontig = 1;
+            g.B = s->Y; g.ldb = ld; g.b_kcontig = 1;
+            g.C = s->L + (int64_t)first * TILE * ld; g.ldc = ld;
+            g.lower_only = 1; g.kmode = 1;
+            g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = 0; g.k_gt0 = 0;
+            PIGP_TRY(launch_gemm(g, st));
+        }
+        PIGP_TRY(launch_grad(p, s->d_tiles, s->n_tiles, theta_dev, s->L, ld, s->alpha, s->partials, s->gpart, st));
+        {
+            PeerBufs pb{};
+            pb.n = c.npeers;
+            for (int q = 0; q < c.npeers; ++q) pb.p[q] = s->peer(c.others[q], s->gslots);
+            ProfScope prof(PROF_GRAD, st);
+            k_push_vec<<<1, 32, 0, st>>>(s->gpart, p->theta_len, s->rank, s->gslots, pb);
+            count_launch();
+        }
+        PIGP_CUDA(cudaGetLastError());
+        PIGP_TRY(signal(c, s->f_grad(s->rank)));
+        PIGP_TRY(wait_all(c, s->f_grad(0)));
+        k_sum_slots<<<1, 32, 0, st>>>(s->gslots, s->world, p->theta_len, grad_dev, info, s->err);
+        count_launch();
+        PIGP_CUDA(cudaGetLastError());
+    }
+    if (info_dev) PIGP_CUDA(cudaMemcpyAsync(info_dev, info, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    return PIGP_OK;
+}
+
+int pigp_dsolver_nll_grad_host(pigp_dsolver* s, const double* theta_host, const double* y_host, double eps, int want_grad,
+                               double* nll_host, double* grad_host, int32_t* info_host) {
+    if (!s || !theta_host || !y_host || !nll_host || (want_grad && !grad_host)) { set_error("pigp_dsolver_nll_grad_host: null argument"); return PIGP_EINVAL; }
+    const int P = s->plan->theta_len;
+    cudaStream_t st = s->own_stream;
+    double* h_theta = s->h_res + 4 + MAX_THETA;
+    double* h_y = h_theta + MAX_THETA;
+    std::memcpy(h_theta, theta_host, sizeof(double) * P);
+    std::memcpy(h_y, y_host, sizeof(double) * s->n);
+    PIGP_CUDA(cudaMemcpyAsync(s->d_theta, h_theta, sizeof(double) * P, cudaMemcpyHostToDevice, st));
+    PIGP_CUDA(cudaMemcpyAsync(s->d_y, h_y, sizeof(double) * s->n, cudaMemcpyHostToDevice, st));
+    PIGP_TRY(pigp_dsolver_nll_grad(s, s->d_theta, s->d_y, eps, s->d_res, want_grad ? s->d_res + 1 : nullptr, nullptr, st));
+    PIGP_CUDA(cudaMemcpyAsync(s->h_res, s->d_res, sizeof(double) * (1 + (want_grad ? P : 0)), cudaMemcpyDeviceToHost, st));
+    int32_t* h_info = reinterpret_cast<int32_t*>(s->h_res + 1 + MAX_THETA);
+    PIGP_CUDA(cudaMemcpyAsync(h_info, s->info, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PIGP_CUDA(cudaMemcpyAsync(h_info + 1, s->err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PIGP_CUDA(cudaStreamSynchronize(st));
+    *nll_host = s->h_res[0];
+    if (want_grad) std::memcpy(grad_host, s->h_res + 1, sizeof(double) * P);
+    if (info_host) *info_host = h_info[0];
+    if (h_info[1] != 0) { set_error("pigp_dsolver: a peer flag wait timed out (a rank is missing or failed)"); return PIGP_ECUDA; }
+    return PIGP_OK;
+}
+
+}  // extern "C"

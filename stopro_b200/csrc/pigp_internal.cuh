@@ -95,8 +95,11 @@ int launch_assemble(const pigp_plan* p, const AsmTile* tiles, int64_t n_tiles, c
 int launch_pad(double* K, int64_t ld, int64_t rows, int64_t cols, int64_t rows_pad, int64_t cols_pad, int unit_diag,
                int lower_only, cudaStream_t st);
 // partials[n_tiles_lower][MAX_THETA] <- per-tile sums of (X - alpha alpha^T) * dK/dtheta ; then reduce into grad
-int launch_grad(const pigp_plan* p, const double* theta_dev, const double* X, int64_t ld, const double* alpha,
-                double* partials, double* grad_out, cudaStream_t st);
+int launch_grad(const pigp_plan* p, const AsmTile* tiles, int64_t n_tiles, const double* theta_dev, const double* X, int64_t ld,
+                const double* alpha, double* partials, double* grad_out, cudaStream_t st);
+// lower-triangle tiles of a symmetric plan whose 128-row tile belongs to `rank` (tile t -> rank t mod world); tiles never
+// straddle a 128-row boundary
+void build_lower_tiles_owned(const pigp_plan* p, int rank, int world, std::vector<AsmTile>& out);
 
 // ---- dense linear algebra (pigp_dense.cu)
 struct GemmDesc {
@@ -107,8 +110,21 @@ struct GemmDesc {
     double* C; int64_t ldc;
     int lower_only;  // skip tiles with tn > tm
     int kmode;       // 0: all k; 1: k_tile >= m_tile; 2: k_tile <= m_tile
+    // ---- generalised addressing (block-cyclic row tiles; zero-initialised = plain GEMM)
+    int gen;         // 1: rectangular tile raster with the predicates below evaluated on GLOBAL tile indices
+    int m_ts;        // row tile tm lives at rows tm * m_ts * 128 of A and C (0 is read as 1)
+    int m_gt0;       // global tile index of row tile 0:  gm = m_gt0 + tm * m_ts
+    int n_gt0;       // global tile index (128 units) of column 0 of C
+    int k_gt0;       // global tile index of k = 0 (kmode 1: k_tile >= gm, kmode 2: k_tile <= gm, in global tiles)
+    int force_bn128; // one CTA per 128 x 128 tile (required when C aliases A: the CTA reads its rows before it writes them)
+    // ---- stores mirrored into peer memory (NVLink P2P) for row tiles with gm < push_gm_end
+    int npeers;
+    int push_gm_end;
+    double* Cpeer[7];  // the address of C[0][0] in each peer's buffer (same ldc)
 };
 int launch_gemm(const GemmDesc& g, cudaStream_t st);
+struct PeerTiles { int n; double* a[7]; double* invd[7]; };  // peer addresses of the diagonal tile / its inverse
+int launch_potf2(double* A, int64_t ld, double* invd, int32_t* info, int base, const PeerTiles& peers, cudaStream_t st);
 int potrf_lower(double* A, int64_t ld, int64_t n, int64_t m_extra, double* invd, int32_t* info, cudaStream_t st);
 int potri_lower(const double* L, int64_t ld, int64_t n, const double* invd, double* W, double* X, cudaStream_t st);
 // out[0] = sum_{i<n} log A[i*ld+i]; out[1] = sum_{j<n} v[j]^2  (v = row `vrow` of A)
