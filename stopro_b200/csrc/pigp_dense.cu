@@ -220,6 +220,20 @@ __global__ void __launch_bounds__(BN_ * 2, 128 / BN_) k_gemm(GemmDesc g) {
     }
 }
 
+template <int BN_, int STAGES_>
+static int gemm_attrs() {
+    constexpr int SMEM = gemm_smem(BN_, STAGES_);
+    PIGP_CUDA(cudaFuncSetAttribute(k_gemm<true, true, BN_, STAGES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    PIGP_CUDA(cudaFuncSetAttribute(k_gemm<true, false, BN_, STAGES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    PIGP_CUDA(cudaFuncSetAttribute(k_gemm<false, true, BN_, STAGES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    PIGP_CUDA(cudaFuncSetAttribute(k_gemm<false, false, BN_, STAGES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    PIGP_PRELOAD((k_gemm<true, true, BN_, STAGES_>));
+    PIGP_PRELOAD((k_gemm<true, false, BN_, STAGES_>));
+    PIGP_PRELOAD((k_gemm<false, true, BN_, STAGES_>));
+    PIGP_PRELOAD((k_gemm<false, false, BN_, STAGES_>));
+    return PIGP_OK;
+}
+
 static int g_gemm_bn = 0;  // 0: read PIGP_GEMM_BN once (kernel tuning); 128 or 64
 
 template <int BN_, int STAGES_>
@@ -229,12 +243,8 @@ static int launch_gemm_cfg(const GemmDesc& d, cudaStream_t st) {
     int dev = 0;
     PIGP_CUDA(cudaGetDevice(&dev));
     bool& attr_set = attr_done[dev & 63];
-    auto set_attr = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); };
     if (!attr_set) {
-        PIGP_CUDA(set_attr(k_gemm<true, true, BN_, STAGES_>));
-        PIGP_CUDA(set_attr(k_gemm<true, false, BN_, STAGES_>));
-        PIGP_CUDA(set_attr(k_gemm<false, true, BN_, STAGES_>));
-        PIGP_CUDA(set_attr(k_gemm<false, false, BN_, STAGES_>));
+        PIGP_TRY((gemm_attrs<BN_, STAGES_>()));
         attr_set = true;
     }
     const bool tri = d.lower_only && !d.gen;
@@ -696,6 +706,19 @@ int launch_gemv(const double* A, int64_t ld, int64_t m, int64_t n, const double*
     k_gemv<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(A, ld, m, n, x, y);
     count_launch();
     PIGP_CUDA(cudaGetLastError());
+    return PIGP_OK;
+}
+
+int preload_dense() {
+    PIGP_TRY((gemm_attrs<128, 4>()));
+    PIGP_TRY((gemm_attrs<64, 3>()));
+    PIGP_CUDA(cudaFuncSetAttribute(k_potf2, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM));
+    PIGP_PRELOAD(k_potf2);
+    PIGP_PRELOAD(k_place_diag);
+    PIGP_PRELOAD(k_logdet_quad);
+    PIGP_PRELOAD(k_trmv_lower_t);
+    PIGP_PRELOAD(k_sum_chunks);
+    PIGP_PRELOAD(k_gemv);
     return PIGP_OK;
 }
 

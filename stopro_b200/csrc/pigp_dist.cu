@@ -341,6 +341,15 @@ int trtri_rec(const Ctx& c, int c0, int nt) {
     return trtri_rec(c, c0 + n1, n2);
 }
 
+int preload_dist() {
+    PIGP_TRY(preload_dense());
+    PIGP_TRY(preload_assemble());
+    PIGP_PRELOAD(k_signal); PIGP_PRELOAD(k_wait); PIGP_PRELOAD(k_push_rows); PIGP_PRELOAD(k_place_diag_t);
+    PIGP_PRELOAD(k_gemv_upper); PIGP_PRELOAD(k_set_ytile); PIGP_PRELOAD(k_push_vec); PIGP_PRELOAD(k_sum_slots);
+    PIGP_PRELOAD(k_finish_nll_d); PIGP_PRELOAD(k_diag_info); PIGP_PRELOAD(k_copy_v);
+    return PIGP_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -360,6 +369,7 @@ int pigp_dsolver_create(pigp_plan* plan, int rank, int world, pigp_dsolver** out
         return PIGP_EINVAL;
     }
     *out = nullptr;
+    PIGP_TRY(preload_dist());
     pigp_dsolver* s = new pigp_dsolver();
     s->plan = plan; s->rank = rank; s->world = world;
     s->n = plan->rows;

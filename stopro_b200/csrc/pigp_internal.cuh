@@ -45,6 +45,16 @@ struct ProfScope {
     ~ProfScope() { if (on) prof_push(cls, st, false, 0.0); }
 };
 
+// Force-load a kernel (CUDA loads kernels lazily on first launch, and that load can block behind a spinning flag wait
+// of another rank that shares the process): every kernel is touched once when a multi-rank solver is created.
+#define PIGP_PRELOAD(f)                                        \
+    do {                                                       \
+        cudaFuncAttributes _a;                                 \
+        PIGP_CUDA(cudaFuncGetAttributes(&_a, f));              \
+    } while (0)
+int preload_dense();
+int preload_assemble();
+
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 // One rectangle of the output matrix, evaluated by one CTA of the assembly / gradient kernels.

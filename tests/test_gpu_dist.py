@@ -58,8 +58,9 @@ CASES = {
     "poiseuille_additive": lambda: dict(synthetic.poiseuille(kernel_form="additive"), eps=1e-2),
     "sinusoidal": lambda: dict(synthetic.sinusoidal(u_num=16, f_nx=14, f_ny=8, dif_num=9, n_test=10), eps=1e-2),
     "sin1d_naive": lambda: synthetic.sin_1d_naive(),                                                   # N = 32: one tile, noise theta
-    "scaling_1280": lambda: synthetic.stokes2d_scaling(1280, n_test=8),                                # N multiple of 128
-    "scaling_1500": lambda: synthetic.stokes2d_scaling(1500, n_test=8),
+    # eps = 1 keeps cond(K) * u below 1e-8 (the 4th-derivative blocks have entries ~ 1e5), so the strict bar applies
+    "scaling_1280": lambda: dict(synthetic.stokes2d_scaling(1280, n_test=8), eps=1.0),                 # N multiple of 128
+    "scaling_1500": lambda: dict(synthetic.stokes2d_scaling(1500, n_test=8), eps=1.0),
 }
 
 
@@ -89,7 +90,7 @@ def test_sharded_matches_oracle(cuda_device, name, world):
 
 
 def test_sharded_matches_single_solver(cuda_device):
-    cfg = synthetic.stokes2d_scaling(3000, n_test=8)
+    cfg = dict(synthetic.stokes2d_scaling(3000, n_test=8), eps=1.0)
     gp = synthetic.make_model(cfg)
     args = (cfg["r_train"], cfg["delta_y"], cfg["eps"])
     nll1, g1 = gp.value_and_grad(cfg["theta0"], *args)
