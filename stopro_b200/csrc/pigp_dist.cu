@@ -183,6 +183,11 @@ struct pigp_dsolver {
     int* err = nullptr;
     double *d_theta = nullptr, *d_y = nullptr, *d_res = nullptr, *h_res = nullptr;
     cudaStream_t own_stream = nullptr;  // the _host entry point runs here (ranks sharing a process must not share a stream)
+    // internal streams: `sa` (high priority) carries the latency-bound Cholesky chain, `sb` the Y = L^-T products that
+    // depend only on finished panels, so that they fill the bubbles of the chain
+    cudaStream_t sa = nullptr, sb = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_bar = nullptr, ev_b = nullptr, ev_out = nullptr;
+    std::vector<cudaEvent_t> ev_diag, ev_upd;
 
     int f_diag(int k) const { return k; }
     int f_panel(int k, int src) const { return T + k * world + src; }
@@ -199,7 +204,9 @@ namespace {
 
 struct Ctx {
     pigp_dsolver* s;
-    cudaStream_t st;
+    cudaStream_t st;   // chain stream
+    cudaStream_t sb;   // side stream (Y = L^-T), used when grad is set
+    bool grad;
     PeerFlags pf;
     int npeers;
     int others[7];
@@ -249,12 +256,14 @@ void set_push(const Ctx& c, GemmDesc& g, double* Cbase) {
     for (int k = 0; k < c.npeers; ++k) g.Cpeer[k] = c.s->peer(c.others[k], Cbase);
 }
 
-// ---- Cholesky over column tiles [c0, c0 + nt)
-int chol_leaf(const Ctx& c, int k) {
+// ---- merged recursion over column tiles [c0, c0 + nt): Cholesky on the chain stream; when the gradient is wanted,
+// the products of Y = L^-T that depend only on finished panels are issued on the side stream behind events.
+int leaf(const Ctx& c, int k) {
     pigp_dsolver* s = c.s;
     const int64_t ld = s->ld;
     double* invk = s->invd + (int64_t)k * TILE * TILE;
-    if (k % s->world == s->rank) {
+    const bool mine = (k % s->world == s->rank);
+    if (mine) {
         double* Akk = s->L + (int64_t)k * TILE * ld + (int64_t)k * TILE;
         PeerTiles pt{};
         pt.n = c.npeers;
@@ -264,81 +273,91 @@ int chol_leaf(const Ctx& c, int k) {
     } else {
         PIGP_TRY(wait_one(c, s->f_diag(k)));
     }
-    const int first = s->first_own(k + 1), cnt = s->count_own(k + 1, s->gy + 1);
-    if (cnt > 0) {
-        GemmDesc g{};
-        g.M = cnt * TILE; g.N = TILE; g.K = TILE;
-        g.alpha = 1.0; g.beta = 0.0;
-        double* Cb = s->L + (int64_t)first * TILE * ld + (int64_t)k * TILE;
-        g.A = Cb; g.lda = ld; g.a_kcontig = 1;
-        g.B = invk; g.ldb = TILE; g.b_kcontig = 1;
-        g.C = Cb; g.ldc = ld;
-        g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = k; g.k_gt0 = k;
-        g.force_bn128 = 1;  // in place
-        set_push(c, g, Cb);
-        PIGP_TRY(launch_gemm(g, c.st));
-    }
-    return signal(c, s->f_panel(k, s->rank));
-}
-
-int chol_rec(const Ctx& c, int c0, int nt) {
-    pigp_dsolver* s = c.s;
-    if (nt == 1) return chol_leaf(c, c0);
-    const int n1 = nt / 2, n2 = nt - n1;
-    PIGP_TRY(chol_rec(c, c0, n1));
-    PIGP_TRY(wait_all(c, s->f_panel(c0 + n1 - 1, 0)));
-    const int first = s->first_own(c0 + n1), cnt = s->count_own(c0 + n1, s->gy + 1);
-    if (cnt > 0) {
-        const int64_t ld = s->ld;
-        GemmDesc g{};
-        g.M = cnt * TILE; g.N = n2 * TILE; g.K = n1 * TILE;
-        g.alpha = -1.0; g.beta = 1.0;
-        g.A = s->L + (int64_t)first * TILE * ld + (int64_t)c0 * TILE; g.lda = ld; g.a_kcontig = 1;
-        g.B = s->L + (int64_t)(c0 + n1) * TILE * ld + (int64_t)c0 * TILE; g.ldb = ld; g.b_kcontig = 1;
-        g.C = s->L + (int64_t)first * TILE * ld + (int64_t)(c0 + n1) * TILE; g.ldc = ld;
-        g.lower_only = 1;
-        g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = c0 + n1; g.k_gt0 = c0;
-        PIGP_TRY(launch_gemm(g, c.st));
-    }
-    return chol_rec(c, c0 + n1, n2);
-}
-
-// ---- Y = L^-T on own row tiles, column tiles [c0, c0 + nt)
-int trtri_rec(const Ctx& c, int c0, int nt) {
-    pigp_dsolver* s = c.s;
-    const int64_t ld = s->ld;
-    if (nt == 1) {
-        const int first = s->first_own(0), cnt = s->count_own(0, c0);  // own rows strictly above the diagonal tile
+    if (c.grad) PIGP_CUDA(cudaEventRecord(s->ev_diag[k], c.st));
+    {
+        // L_ik = A_ik inv(L_kk)^T for the own row tiles below (and the y tile), mirrored into every peer
+        const int first = s->first_own(k + 1), cnt = s->count_own(k + 1, s->gy + 1);
         if (cnt > 0) {
             GemmDesc g{};
             g.M = cnt * TILE; g.N = TILE; g.K = TILE;
             g.alpha = 1.0; g.beta = 0.0;
-            double* Cb = s->Y + (int64_t)first * TILE * ld + (int64_t)c0 * TILE;
+            double* Cb = s->L + (int64_t)first * TILE * ld + (int64_t)k * TILE;
             g.A = Cb; g.lda = ld; g.a_kcontig = 1;
-            g.B = s->invd + (int64_t)c0 * TILE * TILE; g.ldb = TILE; g.b_kcontig = 1;
+            g.B = invk; g.ldb = TILE; g.b_kcontig = 1;
             g.C = Cb; g.ldc = ld;
-            g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = c0; g.k_gt0 = c0;
-            g.force_bn128 = 1;
+            g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = k; g.k_gt0 = k;
+            g.force_bn128 = 1;  // in place
+            set_push(c, g, Cb);
             PIGP_TRY(launch_gemm(g, c.st));
         }
-        return PIGP_OK;
+        PIGP_TRY(signal(c, s->f_panel(k, s->rank)));
     }
+    if (c.grad) {
+        // Y[j, k] = R[j, k] inv(L_kk)^T for own row tiles j < k; Y[k, k] = inv(L_kk)^T
+        PIGP_CUDA(cudaStreamWaitEvent(c.sb, s->ev_diag[k], 0));
+        if (mine) {
+            ProfScope prof(PROF_MISC, c.sb);
+            k_place_diag_t<<<1, 256, 0, c.sb>>>(s->Y, ld, s->invd, k, 1);
+            count_launch();
+            PIGP_CUDA(cudaGetLastError());
+        }
+        const int first = s->first_own(0), cnt = s->count_own(0, k);
+        if (cnt > 0) {
+            GemmDesc g{};
+            g.M = cnt * TILE; g.N = TILE; g.K = TILE;
+            g.alpha = 1.0; g.beta = 0.0;
+            double* Cb = s->Y + (int64_t)first * TILE * ld + (int64_t)k * TILE;
+            g.A = Cb; g.lda = ld; g.a_kcontig = 1;
+            g.B = invk; g.ldb = TILE; g.b_kcontig = 1;
+            g.C = Cb; g.ldc = ld;
+            g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = k; g.k_gt0 = k;
+            g.force_bn128 = 1;
+            PIGP_TRY(launch_gemm(g, c.sb));
+        }
+    }
+    return PIGP_OK;
+}
+
+int rec(const Ctx& c, int c0, int nt) {
+    pigp_dsolver* s = c.s;
+    if (nt == 1) return leaf(c, c0);
+    const int64_t ld = s->ld;
     const int n1 = nt / 2, n2 = nt - n1;
-    PIGP_TRY(trtri_rec(c, c0, n1));
-    const int first = s->first_own(0), cnt = s->count_own(0, c0 + n1);
-    if (cnt > 0) {
-        // Y[j, J2] -= sum_{k in K1, k >= j} Y[j, k] L[J2, k]^T
-        GemmDesc g{};
-        g.M = cnt * TILE; g.N = n2 * TILE; g.K = n1 * TILE;
-        g.alpha = -1.0; g.beta = 1.0;
-        g.A = s->Y + (int64_t)first * TILE * ld + (int64_t)c0 * TILE; g.lda = ld; g.a_kcontig = 1;
-        g.B = s->L + (int64_t)(c0 + n1) * TILE * ld + (int64_t)c0 * TILE; g.ldb = ld; g.b_kcontig = 1;
-        g.C = s->Y + (int64_t)first * TILE * ld + (int64_t)(c0 + n1) * TILE; g.ldc = ld;
-        g.kmode = 1;
-        g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = c0 + n1; g.k_gt0 = c0;
-        PIGP_TRY(launch_gemm(g, c.st));
+    PIGP_TRY(rec(c, c0, n1));
+    PIGP_TRY(wait_all(c, s->f_panel(c0 + n1 - 1, 0)));  // every peer's rows of the panels [c0, c0 + n1) have arrived
+    if (c.grad) PIGP_CUDA(cudaEventRecord(s->ev_upd[c0 + n1 - 1], c.st));
+    {
+        // trailing update of the own row tiles: C[i, J2] -= L[i, K1] L[J2, K1]^T (lower part)
+        const int first = s->first_own(c0 + n1), cnt = s->count_own(c0 + n1, s->gy + 1);
+        if (cnt > 0) {
+            GemmDesc g{};
+            g.M = cnt * TILE; g.N = n2 * TILE; g.K = n1 * TILE;
+            g.alpha = -1.0; g.beta = 1.0;
+            g.A = s->L + (int64_t)first * TILE * ld + (int64_t)c0 * TILE; g.lda = ld; g.a_kcontig = 1;
+            g.B = s->L + (int64_t)(c0 + n1) * TILE * ld + (int64_t)c0 * TILE; g.ldb = ld; g.b_kcontig = 1;
+            g.C = s->L + (int64_t)first * TILE * ld + (int64_t)(c0 + n1) * TILE; g.ldc = ld;
+            g.lower_only = 1;
+            g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = c0 + n1; g.k_gt0 = c0;
+            PIGP_TRY(launch_gemm(g, c.st));
+        }
     }
-    return trtri_rec(c, c0 + n1, n2);
+    if (c.grad) {
+        // Y[j, J2] -= sum_{k in K1, k >= j} Y[j, k] L[J2, k]^T for the own row tiles j < c0 + n1
+        PIGP_CUDA(cudaStreamWaitEvent(c.sb, s->ev_upd[c0 + n1 - 1], 0));
+        const int first = s->first_own(0), cnt = s->count_own(0, c0 + n1);
+        if (cnt > 0) {
+            GemmDesc g{};
+            g.M = cnt * TILE; g.N = n2 * TILE; g.K = n1 * TILE;
+            g.alpha = -1.0; g.beta = 1.0;
+            g.A = s->Y + (int64_t)first * TILE * ld + (int64_t)c0 * TILE; g.lda = ld; g.a_kcontig = 1;
+            g.B = s->L + (int64_t)(c0 + n1) * TILE * ld + (int64_t)c0 * TILE; g.ldb = ld; g.b_kcontig = 1;
+            g.C = s->Y + (int64_t)first * TILE * ld + (int64_t)(c0 + n1) * TILE; g.ldc = ld;
+            g.kmode = 1;
+            g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = c0 + n1; g.k_gt0 = c0;
+            PIGP_TRY(launch_gemm(g, c.sb));
+        }
+    }
+    return rec(c, c0 + n1, n2);
 }
 
 int preload_dist() {
@@ -360,6 +379,11 @@ void pigp_dsolver_destroy(pigp_dsolver* s) {
     cudaFree(s->alpha); cudaFree(s->info); cudaFree(s->err); cudaFree(s->d_theta); cudaFree(s->d_y); cudaFree(s->d_res);
     if (s->h_res) cudaFreeHost(s->h_res);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    if (s->sa) cudaStreamDestroy(s->sa);
+    if (s->sb) cudaStreamDestroy(s->sb);
+    for (cudaEvent_t e : {s->ev_in, s->ev_bar, s->ev_b, s->ev_out}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : s->ev_diag) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : s->ev_upd) if (e) cudaEventDestroy(e);
     delete s;
 }
 
@@ -420,6 +444,19 @@ int pigp_dsolver_create(pigp_plan* plan, int rank, int world, pigp_dsolver** out
     cuda_ok(cudaMalloc(&s->d_res, sizeof(double) * (1 + MAX_THETA)), "cudaMalloc res");
     cuda_ok(cudaMallocHost(&s->h_res, sizeof(double) * (4 + 2 * MAX_THETA) + sizeof(double) * s->n), "cudaMallocHost res");
     cuda_ok(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    {
+        int lo = 0, hi = 0;
+        cuda_ok(cudaDeviceGetStreamPriorityRange(&lo, &hi), "cudaDeviceGetStreamPriorityRange");
+        cuda_ok(cudaStreamCreateWithPriority(&s->sa, cudaStreamNonBlocking, hi), "cudaStreamCreate sa");
+        cuda_ok(cudaStreamCreateWithPriority(&s->sb, cudaStreamNonBlocking, lo), "cudaStreamCreate sb");
+        for (cudaEvent_t* e : {&s->ev_in, &s->ev_bar, &s->ev_b, &s->ev_out}) cuda_ok(cudaEventCreateWithFlags(e, cudaEventDisableTiming), "cudaEventCreate");
+        s->ev_diag.assign(s->T, nullptr);
+        s->ev_upd.assign(s->T, nullptr);
+        for (int k = 0; k < s->T; ++k) {
+            cuda_ok(cudaEventCreateWithFlags(&s->ev_diag[k], cudaEventDisableTiming), "cudaEventCreate");
+            cuda_ok(cudaEventCreateWithFlags(&s->ev_upd[k], cudaEventDisableTiming), "cudaEventCreate");
+        }
+    }
     if (rc != PIGP_OK) { pigp_dsolver_destroy(s); return rc; }
     s->connected = (world == 1);
     *out = s;
@@ -481,16 +518,29 @@ int pigp_dsolver_nll_grad(pigp_dsolver* s, const double* theta_dev, const double
                           double* grad_dev, int32_t* info_dev, void* stream) {
     if (!s || !theta_dev || !y_dev || !nll_dev) { set_error("pigp_dsolver_nll_grad: null argument"); return PIGP_EINVAL; }
     if (!s->connected) { set_error("pigp_dsolver_nll_grad: peers are not connected"); return PIGP_EINVAL; }
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+    cudaStream_t st = s->sa;
     const pigp_plan* p = s->plan;
     const int64_t ld = s->ld;
     s->epoch += 1;
     Ctx c = make_ctx(s, st);
+    c.sb = s->sb;
+    c.grad = grad_dev != nullptr;
     int32_t* info = s->info;
+    PIGP_CUDA(cudaEventRecord(s->ev_in, user));
+    PIGP_CUDA(cudaStreamWaitEvent(st, s->ev_in, 0));
     PIGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
     // every peer has finished reading what the previous call left in this rank's buffers
     PIGP_TRY(signal(c, s->f_bar(s->rank)));
     PIGP_TRY(wait_all(c, s->f_bar(0)));
+    const int first = s->first_own(0), cnt = s->count_own(0, s->T);
+    if (c.grad) {
+        PIGP_CUDA(cudaEventRecord(s->ev_bar, st));
+        PIGP_CUDA(cudaStreamWaitEvent(s->sb, s->ev_bar, 0));
+        if (cnt > 0)
+            PIGP_CUDA(cudaMemset2DAsync(s->Y + (int64_t)first * TILE * ld, sizeof(double) * TILE * ld * s->world, 0,
+                                        sizeof(double) * TILE * ld, cnt, s->sb));
+    }
     // own rows of K (lower, jitter added), identity padding (owner of the last tile), own y tile
     PIGP_TRY(launch_assemble(p, s->d_tiles, s->n_tiles, theta_dev, eps, 1, s->L, ld, st));
     if (s->n < s->npad && (s->T - 1) % s->world == s->rank)
@@ -502,27 +552,18 @@ int pigp_dsolver_nll_grad(pigp_dsolver* s, const double* theta_dev, const double
         count_launch();
     }
     PIGP_CUDA(cudaGetLastError());
-    PIGP_TRY(chol_rec(c, 0, s->T));
-    // every rank holds all of L now (the last panel flags of every peer were awaited inside chol_rec for all but the
-    // final leaf; the final diagonal tile arrives with its DIAG flag)
+    PIGP_TRY(rec(c, 0, s->T));
+    // every rank holds all of L now (the panel flags of every peer were awaited inside rec for all but the final leaf,
+    // whose diagonal tile arrives with its DIAG flag)
     PIGP_TRY(launch_logdet_quad(s->L, ld, s->n, ytile, s->out2, st));
     k_diag_info<<<1, 1024, 0, st>>>(s->L, ld, s->n, info);
     count_launch();
     k_finish_nll_d<<<1, 1, 0, st>>>(s->out2, s->n, info, s->err, nll_dev);
     count_launch();
     PIGP_CUDA(cudaGetLastError());
-    if (grad_dev) {
-        // Y = L^-T on own row tiles
-        const int first = s->first_own(0), cnt = s->count_own(0, s->T);
-        if (cnt > 0) {
-            PIGP_CUDA(cudaMemset2DAsync(s->Y + (int64_t)first * TILE * ld, sizeof(double) * TILE * ld * s->world, 0,
-                                        sizeof(double) * TILE * ld, cnt, st));
-            ProfScope prof(PROF_MISC, st);
-            k_place_diag_t<<<cnt, 256, 0, st>>>(s->Y, ld, s->invd, first, s->world);
-            count_launch();
-        }
-        PIGP_CUDA(cudaGetLastError());
-        PIGP_TRY(trtri_rec(c, 0, s->T));
+    if (c.grad) {
+        PIGP_CUDA(cudaEventRecord(s->ev_b, s->sb));
+        PIGP_CUDA(cudaStreamWaitEvent(st, s->ev_b, 0));  // own rows of Y are complete
         if (c.npeers > 0) {
             if (cnt > 0) {
                 PeerBufs pb{};
@@ -573,6 +614,8 @@ int pigp_dsolver_nll_grad(pigp_dsolver* s, const double* theta_dev, const double
         PIGP_CUDA(cudaGetLastError());
     }
     if (info_dev) PIGP_CUDA(cudaMemcpyAsync(info_dev, info, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    PIGP_CUDA(cudaEventRecord(s->ev_out, st));
+    PIGP_CUDA(cudaStreamWaitEvent(user, s->ev_out, 0));
     return PIGP_OK;
 }
 

@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# tests/test_gpu_dist.py runs several ranks (3 streams each, with spinning flag waits) inside one process: every stream
+# needs its own hardware queue or a wait in one stream stalls an unrelated one (the default is 8 queues per process)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -5,6 +5,8 @@
 """
 import os
 import sys
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import threading
 import time
 
