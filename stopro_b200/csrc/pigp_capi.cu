@@ -109,18 +109,6 @@ __global__ void k_set_yrow(double* A, int64_t ld, int64_t n, int64_t npad, int64
     }
 }
 
-__global__ void k_extract_v(const double* row, int64_t n, int64_t npad, double* v) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < npad) v[i] = (i < n) ? row[i] : 0.0;
-}
-
-__global__ void k_finish_nll(const double* out2, int64_t n, const int32_t* info, double* nll) {
-    // GP/gp.py:85-89
-    double v = 0.5 * out2[1] + out2[0] + 0.5 * (double)n * log(2.0 * 3.14159265358979323846);
-    if (info && *info != 0) v = nan("");
-    *nll = v;
-}
-
 __global__ void k_rowsumsq_sub(const double* Vt, int64_t ld, int64_t m, int64_t n, const double* kdiag, double* var) {
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= m) return;
@@ -146,6 +134,7 @@ using namespace pigp;
 
 struct pigp_solver {
     pigp_plan* plan = nullptr;
+    pigp_dsolver* ds = nullptr;  // world = 1 instance of the block-cyclic solver: NLL and gradient run there
     int64_t n = 0, npad = 0;
     int64_t yrow = 0;        // row of the factorisation buffer that carries y
     int64_t mrow0 = 0;       // first row available to the mixed (test x train) block
@@ -365,6 +354,7 @@ int pigp_assemble_host(pigp_plan* p, const double* theta_host, double eps, int a
 // ------------------------------------------------------------------------------------------------ solver
 void pigp_solver_destroy(pigp_solver* s) {
     if (!s) return;
+    pigp_dsolver_destroy(s->ds);
     cudaFree(s->A); cudaFree(s->W); cudaFree(s->invd); cudaFree(s->v); cudaFree(s->alpha); cudaFree(s->trmv_part);
     cudaFree(s->partials); cudaFree(s->out2); cudaFree(s->info); cudaFree(s->T); cudaFree(s->d_theta); cudaFree(s->d_y);
     cudaFree(s->d_res); cudaFree(s->d_mu);
@@ -391,16 +381,12 @@ int pigp_solver_create(pigp_plan* plan, pigp_solver** out) {
     s->npad = round_up(s->n, TILE);
     if (s->n < s->npad) { s->yrow = s->n; s->mrow0 = s->npad; }          // y rides in the first padding row
     else { s->yrow = s->npad; s->mrow0 = s->npad + TILE; }                // no padding row: y gets its own block
-    int rc = ensure_rows(s, s->mrow0);
+    int rc = pigp_dsolver_create(plan, 0, 1, &s->ds);  // A (posterior only) is allocated on first use
     auto cuda_ok = [&](cudaError_t e, const char* what) {
         if (e != cudaSuccess && rc == PIGP_OK) { set_error(std::string(what) + ": " + cudaGetErrorString(e)); rc = PIGP_ECUDA; }
     };
     const int64_t nt = s->npad / TILE;
     cuda_ok(cudaMalloc(&s->invd, sizeof(double) * nt * TILE * TILE), "cudaMalloc invd");
-    cuda_ok(cudaMalloc(&s->v, sizeof(double) * s->npad), "cudaMalloc v");
-    cuda_ok(cudaMalloc(&s->alpha, sizeof(double) * s->npad), "cudaMalloc alpha");
-    cuda_ok(cudaMalloc(&s->trmv_part, sizeof(double) * ((s->npad + 1023) / 1024) * s->npad), "cudaMalloc trmv_part");
-    cuda_ok(cudaMalloc(&s->partials, sizeof(double) * std::max<int64_t>(plan->n_tiles_lower, 1) * MAX_THETA), "cudaMalloc partials");
     cuda_ok(cudaMalloc(&s->out2, sizeof(double) * 2), "cudaMalloc out2");
     cuda_ok(cudaMalloc(&s->info, sizeof(int32_t)), "cudaMalloc info");
     cuda_ok(cudaMalloc(&s->d_theta, sizeof(double) * MAX_THETA), "cudaMalloc theta");
@@ -431,38 +417,16 @@ static int factor(pigp_solver* s, const double* theta, const double* y, double e
     return potrf_lower(s->A, ld, s->npad, (s->mrow0 - s->npad) + extra_rows, s->invd, info, st);
 }
 
-static int nll_from_factor(pigp_solver* s, const int32_t* info, double* nll_out, cudaStream_t st) {
-    PIGP_TRY(launch_logdet_quad(s->A, s->npad, s->n, s->A + s->yrow * s->npad, s->out2, st));
-    k_finish_nll<<<1, 1, 0, st>>>(s->out2, s->n, info, nll_out);
-    count_launch();
-    PIGP_CUDA(cudaGetLastError());
-    return PIGP_OK;
-}
-
 int pigp_nll(pigp_solver* s, const double* theta_dev, const double* y_dev, double eps, double* out_dev, int32_t* info_dev,
              void* stream) {
     if (!s || !theta_dev || !y_dev || !out_dev) { set_error("pigp_nll: null argument"); return PIGP_EINVAL; }
-    cudaStream_t st = as_stream(stream);
-    int32_t* info = info_dev ? info_dev : s->info;
-    PIGP_TRY(factor(s, theta_dev, y_dev, eps, 0, info, st));
-    return nll_from_factor(s, info, out_dev, st);
+    return pigp_dsolver_nll_grad(s->ds, theta_dev, y_dev, eps, out_dev, nullptr, info_dev ? info_dev : s->info, stream);
 }
 
 int pigp_nll_grad(pigp_solver* s, const double* theta_dev, const double* y_dev, double eps, double* nll_dev, double* grad_dev,
                   int32_t* info_dev, void* stream) {
     if (!s || !theta_dev || !y_dev || !nll_dev || !grad_dev) { set_error("pigp_nll_grad: null argument"); return PIGP_EINVAL; }
-    cudaStream_t st = as_stream(stream);
-    int32_t* info = info_dev ? info_dev : s->info;
-    if (!s->W) PIGP_CUDA(cudaMalloc(&s->W, sizeof(double) * (size_t)s->npad * s->npad));
-    PIGP_TRY(factor(s, theta_dev, y_dev, eps, 0, info, st));
-    PIGP_TRY(nll_from_factor(s, info, nll_dev, st));
-    k_extract_v<<<(unsigned)((s->npad + 255) / 256), 256, 0, st>>>(s->A + s->yrow * s->npad, s->n, s->npad, s->v);
-    count_launch();
-    PIGP_CUDA(cudaGetLastError());
-    // K^-1 over the factor (the y row / padding rows only add a decoupled identity-like block)
-    PIGP_TRY(potri_lower(s->A, s->npad, s->npad, s->invd, s->W, s->A, st));
-    PIGP_TRY(launch_trmv_lower_t(s->W, s->npad, s->npad, s->v, s->alpha, s->trmv_part, st));
-    return launch_grad(s->plan, s->plan->d_tiles_lower, s->plan->n_tiles_lower, theta_dev, s->A, s->npad, s->alpha, s->partials, grad_dev, st);
+    return pigp_dsolver_nll_grad(s->ds, theta_dev, y_dev, eps, nll_dev, grad_dev, info_dev ? info_dev : s->info, stream);
 }
 
 int pigp_nll_grad_host(pigp_solver* s, const double* theta_host, const double* pts_host, const double* y_host, double eps,
