@@ -180,6 +180,9 @@ int64_t pigp_launch_count(void);
  * returns, per class, the summed kernel time [ms], the number of launches and (GEMM class) the flops executed
  * at tile granularity.  Classes: 0 assemble, 1 gemm (DMMA), 2 potf2, 3 gradient, 4 everything else. */
 #define PIGP_PROF_CLASSES 5
+/* on = 1 (default): the Y = L^-T products run on a side stream concurrently with the Cholesky chain.  on = 0 puts every
+ * kernel on one stream, so that per-launch event times do not overlap (used by the per-class timing pass of bench.py). */
+int pigp_set_side_stream(int on);
 int pigp_profile_start(void);
 int pigp_profile_stop(double* ms_out, int64_t* launches_out, double* flops_out);
 

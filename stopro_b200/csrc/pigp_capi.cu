@@ -16,7 +16,7 @@ void set_error(const std::string& msg) { t_error = msg; }
 std::atomic<long long> g_launches{0};
 
 bool g_prof_on = false;
-struct ProfRec { int cls; cudaEvent_t e0, e1; double flops; int m, n, k, mode; };
+struct ProfRec { int cls; cudaEvent_t e0, e1; double flops; int m, n, k, mode; cudaStream_t st; };
 static int g_note[4] = {0, 0, 0, 0};
 void prof_note(int m, int n, int k, int mode) { g_note[0] = m; g_note[1] = n; g_note[2] = k; g_note[3] = mode; }
 static std::vector<ProfRec> g_prof;
@@ -24,7 +24,7 @@ static std::mutex g_prof_mu;
 void prof_push(int cls, cudaStream_t st, bool begin, double flops) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     if (begin) {
-        ProfRec r{cls, nullptr, nullptr, flops, g_note[0], g_note[1], g_note[2], g_note[3]};
+        ProfRec r{cls, nullptr, nullptr, flops, g_note[0], g_note[1], g_note[2], g_note[3], st};
         g_note[0] = g_note[1] = g_note[2] = g_note[3] = 0;
         cudaEventCreate(&r.e0);
         cudaEventCreate(&r.e1);
@@ -32,7 +32,7 @@ void prof_push(int cls, cudaStream_t st, bool begin, double flops) {
         g_prof.push_back(r);
     } else {
         for (size_t i = g_prof.size(); i-- > 0;)
-            if (g_prof[i].cls == cls) { cudaEventRecord(g_prof[i].e1, st); break; }
+            if (g_prof[i].cls == cls && g_prof[i].st == st && g_prof[i].e1 != nullptr) { cudaEventRecord(g_prof[i].e1, st); break; }
     }
 }
 
@@ -185,14 +185,19 @@ int pigp_profile_stop(double* ms_out, int64_t* launches_out, double* flops_out) 
     }
     FILE* dump = nullptr;
     if (const char* path = getenv("PIGP_PROF_DUMP")) dump = fopen(path, "w");
-    if (dump) fprintf(dump, "class,ms,flops,m,n,k,mode\n");
+    if (dump) fprintf(dump, "class,ms,flops,m,n,k,mode,start_ms,stream\n");
     for (auto& r : g_prof) {
-        float ms = 0.f;
+        float ms = 0.f, t0 = 0.f;
         cudaEventElapsedTime(&ms, r.e0, r.e1);
-        if (dump) fprintf(dump, "%d,%.6f,%.0f,%d,%d,%d,%d\n", r.cls, ms, r.flops, r.m, r.n, r.k, r.mode);
+        if (dump) {
+            cudaEventElapsedTime(&t0, g_prof.front().e0, r.e0);
+            fprintf(dump, "%d,%.6f,%.0f,%d,%d,%d,%d,%.6f,%p\n", r.cls, ms, r.flops, r.m, r.n, r.k, r.mode, t0, (void*)r.st);
+        }
         if (ms_out) ms_out[r.cls] += ms;
         if (launches_out) launches_out[r.cls] += 1;
         if (flops_out) flops_out[r.cls] += r.flops;
+    }
+    for (auto& r : g_prof) {
         cudaEventDestroy(r.e0);
         cudaEventDestroy(r.e1);
     }
@@ -538,6 +543,8 @@ int pigp_potrf_lower(double* A_dev, int64_t ld, int64_t n, int64_t m_extra, doub
     if (info_dev) PIGP_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int32_t), as_stream(stream)));
     return potrf_lower(A_dev, ld, n, m_extra, invd_dev, info_dev, as_stream(stream));
 }
+
+int pigp_debug_potf2_stamps(long long* dev_buf) { return set_potf2_debug(dev_buf); }
 
 int pigp_potri_lower(const double* L_dev, int64_t ld, int64_t n, const double* invd_dev, double* W_dev, double* X_dev, void* stream) {
     if (!L_dev || !invd_dev || !W_dev || !X_dev) { set_error("pigp_potri_lower: null argument"); return PIGP_EINVAL; }

@@ -91,6 +91,24 @@ __device__ __forceinline__ void load_frags(double2* frag, const double* sm, int 
     }
 }
 
+// Bounded spin on epoch flags written by peers (st.release.sys); see pigp_dist.cu.
+__device__ __forceinline__ void wait_flags(const GemmDesc& g, int tid) {
+    if (g.wait_count <= 0) return;
+    if (tid < g.wait_count && tid != g.wait_skip) {
+        const unsigned long long* p = g.wait_flags + g.wait_idx0 + (int64_t)tid * g.wait_stride;
+        unsigned long long t0, now, v;
+        asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t0));
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+            if (v >= g.wait_val) break;
+            asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(now));
+            if (now - t0 > 4000000000ull) { atomicExch(g.wait_err, 1); break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+}
+
 // BN_ = 128: 8 warps, one CTA per SM.  BN_ = 64: 4 warps, two CTAs per SM (independent barriers: while one CTA waits at its
 // barrier or on shared-memory loads, the other keeps the FP64 tensor pipe busy).
 template <bool AKC, bool BKC, int BN_, int STAGES_>
@@ -130,6 +148,7 @@ __global__ void __launch_bounds__(BN_ * 2, 128 / BN_) k_gemm(GemmDesc g) {
     if (g.kmode == 1) kt_begin = max(0, gm - g.k_gt0) * (BM / BK);
     else if (g.kmode == 2) kt_end = min(kt_end, (gm - g.k_gt0 + 1) * (BM / BK));
     if (kt_end <= kt_begin && g.beta == 1.0) return;  // nothing to add
+    wait_flags(g, tid);
 
     double acc[8][4][2];
 #pragma unroll
@@ -234,6 +253,154 @@ static int gemm_attrs() {
     return PIGP_OK;
 }
 
+// ----------------------------------------------------------------------------------------------- small-tile GEMM
+// Same contract as k_gemm for k-contiguous A and B in `gen` addressing, with BM_ x BN_ CTA tiles (BM_ = 32 or 64) for
+// the latency-bound launches of the factorisation (the K = 128 TRSM by the inverse diagonal tile, the low levels of
+// the trailing updates): 4-8 x more CTAs than 128 x 64 tiles, so that a 26-row-tile panel still covers the GPU.
+// BN_ = 128 with N = 128 is safe in place (C aliasing A): a CTA reads all 128 columns of its rows before it writes.
+template <int BM_, int BN_, int STAGES_>
+__global__ void __launch_bounds__(BN_ * 2) k_gemm_s(GemmDesc g) {
+    constexpr int THREADS = BN_ * 2;
+    constexpr int MI = BM_ / 16;  // 8-row MMA tiles per warp (2 warps along M)
+    constexpr int OPA = BM_ * LDS_K, OPB = BN_ * LDS_K, STG = OPA + OPB;
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int wm = warp & 1, wn = warp >> 1;
+
+    const int nt = g.N / BN_, mt = g.M / BM_;
+    const int tn = blockIdx.x % nt, tm = blockIdx.x / nt;
+    if (tm >= mt) return;
+    constexpr int SUB = BM / BM_;                      // CTA row tiles per 128-row tile
+    const int gm = g.m_gt0 + (tm / SUB) * g.m_ts;      // global 128-row tile
+    const int64_t rg = (int64_t)gm * BM + (tm % SUB) * BM_, cg = (int64_t)g.n_gt0 * BM + (int64_t)tn * BN_;
+    if (g.lower_only && cg >= rg + BM_) return;
+    const int64_t m0 = (int64_t)(tm / SUB) * g.m_ts * BM + (tm % SUB) * BM_, n0 = (int64_t)tn * BN_;
+    int kt_begin = 0, kt_end = g.K / BK;
+    if (g.kmode == 1) kt_begin = max(0, gm - g.k_gt0) * (BM / BK);
+    if (kt_end <= kt_begin && g.beta == 1.0) return;
+    wait_flags(g, tid);
+
+    double acc[MI][4][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int nk = kt_end - kt_begin;
+#pragma unroll
+    for (int s = 0; s < STAGES_ - 1; ++s) {
+        if (s < nk) {
+            load_operand<true, BM_, THREADS>(smem + s * STG, g.A, g.lda, m0, (int64_t)(kt_begin + s) * BK, tid);
+            load_operand<true, BN_, THREADS>(smem + s * STG + OPA, g.B, g.ldb, n0, (int64_t)(kt_begin + s) * BK, tid);
+        }
+        cp_async_commit();
+    }
+    for (int it = 0; it < nk; ++it) {
+        cp_async_wait<STAGES_ - 2>();
+        __syncthreads();
+        {
+            const int nx = it + STAGES_ - 1;
+            if (nx < nk) {
+                const int s = nx % STAGES_;
+                load_operand<true, BM_, THREADS>(smem + s * STG, g.A, g.lda, m0, (int64_t)(kt_begin + nx) * BK, tid);
+                load_operand<true, BN_, THREADS>(smem + s * STG + OPA, g.B, g.ldb, n0, (int64_t)(kt_begin + nx) * BK, tid);
+            }
+            cp_async_commit();
+        }
+        const double* sA = smem + (it % STAGES_) * STG;
+        const double* sB = sA + OPA;
+#pragma unroll
+        for (int k8 = 0; k8 < BK; k8 += 8) {
+            double2 af[MI], bf[4];
+            load_frags<true, MI, BM_>(af, sA, wm * (BM_ / 2), k8, gid, tig);
+            load_frags<true, 4, BN_>(bf, sB, wn * 32, k8, gid, tig);
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi].x, bf[ni].x);
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi].y, bf[ni].y);
+        }
+    }
+    cp_async_wait<0>();
+    if (BN_ == 128 && g.C == g.A) __syncthreads();  // in place: every warp has consumed the CTA's rows
+
+    const bool push = g.npeers > 0 && gm < g.push_gm_end;
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi) {
+        const int lr = 8 * mi + gid;
+        double* crow = g.C + (m0 + wm * (BM_ / 2) + lr) * g.ldc + n0 + wn * 32;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int c0 = 16 * q + 2 * tig, c1 = c0 + 8;
+            double2* p0 = reinterpret_cast<double2*>(crow + c0);
+            double2* p1 = reinterpret_cast<double2*>(crow + c1);
+            double2 o0 = make_double2(g.alpha * acc[mi][2 * q][0], g.alpha * acc[mi][2 * q][1]);
+            double2 o1 = make_double2(g.alpha * acc[mi][2 * q + 1][0], g.alpha * acc[mi][2 * q + 1][1]);
+            if (g.beta != 0.0) {
+                const double2 a0 = *p0, a1 = *p1;
+                o0.x = fma(g.beta, a0.x, o0.x); o0.y = fma(g.beta, a0.y, o0.y);
+                o1.x = fma(g.beta, a1.x, o1.x); o1.y = fma(g.beta, a1.y, o1.y);
+            }
+            *p0 = o0;
+            *p1 = o1;
+            if (push) {
+                const int64_t off = (crow - g.C) + c0;
+                for (int p = 0; p < g.npeers; ++p) {
+                    double* qd = g.Cpeer[p] + off;
+                    *reinterpret_cast<double2*>(qd) = o0;
+                    *reinterpret_cast<double2*>(qd + 8) = o1;
+                }
+            }
+        }
+    }
+    if (g.sig_total > 0) {
+        // the last CTA to finish publishes the epoch to the peers (release: all stores above are fenced first)
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int done = atomicAdd(g.sig_counter, 1u);
+            if (done == (unsigned int)g.sig_total - 1u) {
+                *g.sig_counter = 0u;
+                __threadfence_system();
+                for (int p = 0; p < g.sig_n; ++p)
+                    asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(g.sig_flag[p]), "l"(g.sig_val) : "memory");
+            }
+        }
+    }
+}
+
+template <int BM_, int BN_, int STAGES_>
+static int launch_gemm_small(const GemmDesc& d, cudaStream_t st) {
+    constexpr int SMEM = STAGES_ * (BM_ + BN_) * LDS_K * (int)sizeof(double);
+    static bool attr_done[64] = {};
+    int dev = 0;
+    PIGP_CUDA(cudaGetDevice(&dev));
+    if (!attr_done[dev & 63]) {
+        PIGP_CUDA(cudaFuncSetAttribute(k_gemm_s<BM_, BN_, STAGES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr_done[dev & 63] = true;
+    }
+    const int64_t ctas = (int64_t)(d.M / BM_) * (d.N / BN_);
+    double flops = 0.0;
+    if (g_prof_on) {
+        const int kt = d.K / BK, per = BM / BK;
+        for (int t = 0; t < d.M / BM; ++t) {
+            const int gm = d.m_gt0 + t * d.m_ts;
+            const int ncols = d.lower_only ? std::max(0, std::min(d.N / BM, gm - d.n_gt0 + 1)) : d.N / BM;
+            const int kb = d.kmode == 1 ? std::max(0, gm - d.k_gt0) * per : 0;
+            flops += 2.0 * BM * BM * BK * (double)std::max(0, kt - kb) * ncols;
+        }
+        prof_note(d.M, d.N, d.K, 100 + d.kmode * 10 + d.lower_only);
+    }
+    ProfScope prof(PROF_GEMM, st, flops);
+    k_gemm_s<BM_, BN_, STAGES_><<<(unsigned)ctas, BN_ * 2, SMEM, st>>>(d);
+    count_launch();
+    return PIGP_OK;
+}
+
 static int g_gemm_bn = 0;  // 0: read PIGP_GEMM_BN once (kernel tuning); 128 or 64
 
 template <int BN_, int STAGES_>
@@ -287,6 +454,23 @@ int launch_gemm(const GemmDesc& g_in, cudaStream_t st) {
         const char* e = getenv("PIGP_GEMM_BN");
         g_gemm_bn = (e && atoi(e) == 128) ? 128 : 64;
     }
+    static int small_on = -1;
+    if (small_on < 0) { const char* e = getenv("PIGP_GEMM_SMALL"); small_on = (e && atoi(e) == 0) ? 0 : 1; }
+    if (small_on && g.gen && g.a_kcontig && g.b_kcontig && g.kmode != 2) {
+        // latency-bound launches: fewer than one wave of 128 x 64 tiles
+        if (g.force_bn128 && g.N == BM) {
+            PIGP_TRY((launch_gemm_small<32, 128, 3>(g, st)));
+            PIGP_CUDA(cudaGetLastError());
+            return PIGP_OK;
+        }
+        const int64_t tiles = (int64_t)(g.M / BM) * (g.N / 64) / (g.lower_only ? 2 : 1);
+        if (!g.force_bn128 && tiles < 2 * 148) {
+            PIGP_TRY((launch_gemm_small<64, 64, 3>(g, st)));
+            PIGP_CUDA(cudaGetLastError());
+            return PIGP_OK;
+        }
+    }
+    if (g.sig_total > 0) { set_error("pigp gemm: fused signal needs the small-tile kernel"); return PIGP_EINVAL; }
     auto run = [&](const GemmDesc& d) {
         return (g_gemm_bn == 128 || d.force_bn128) ? launch_gemm_cfg<128, 4>(d, st) : launch_gemm_cfg<64, 3>(d, st);
     };
@@ -394,20 +578,26 @@ __device__ __forceinline__ void warp_potrf32(double* D, int ld, double* Winv, in
 // Factor the lower triangle of the 128 x 128 tile at A in place (the upper part of the tile is set to zero) and write
 // inv(L) (lower, zeros above) to invd[128*128].  Non-positive pivot -> *info = base + column + 1 (first one wins)
 // and NaNs propagate, which is what jnp.linalg.cholesky gives the reference.
+__device__ long long* g_potf2_dbg = nullptr;  // optional phase stamps (tools/potf2_bench.py)
+#define POTF2_STAMP(i) do { if (g_potf2_dbg && threadIdx.x == 0) g_potf2_dbg[i] = clock64(); } while (0)
+
 __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double* invd, int32_t* info, int base, PeerTiles peers) {
     extern __shared__ __align__(16) double sm[];
     double* scratch = sm + PT * PLD;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    POTF2_STAMP(0);
     for (int e = tid; e < PT * PT; e += 256) {
         const int i = e >> 7, j = e & 127;
         sm[i * PLD + j] = (j <= i) ? A[(int64_t)i * ld + j] : 0.0;
     }
     __syncthreads();
+    POTF2_STAMP(1);
     for (int kb = 0; kb < 4; ++kb) {
         const int o = 32 * kb;
         double* invk = scratch + kb * 32 * SLD;
         if (warp == 0) warp_potrf32(sm + o * PLD + o, PLD, invk, info, base + o, lane);
         __syncthreads();
+        POTF2_STAMP(2 + 3 * kb);
         const int r_lo = o + 32;
         const int n_strips = (PT - r_lo) / 8;
         // panel: rows below the block, L_ik = A_ik inv(L_kk)^T, in place (a strip is read entirely before it is written)
@@ -416,6 +606,7 @@ __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double*
             strip_mma<false>(X, PLD, X, PLD, invk, SLD, 32, 1.0, false, 4, lane);
         }
         __syncthreads();
+        POTF2_STAMP(3 + 3 * kb);
         // trailing update (lower): tasks = (8-row strip, 32-column group at or left of it)
         int task = 0;
         for (int st = 0; st < n_strips; ++st) {
@@ -429,6 +620,7 @@ __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double*
             }
         }
         __syncthreads();
+        POTF2_STAMP(4 + 3 * kb);
     }
     for (int e = tid; e < PT * PT; e += 256) {
         const int i = e >> 7, j = e & 127;
@@ -436,6 +628,7 @@ __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double*
         A[(int64_t)i * ld + j] = v;
         for (int p = 0; p < peers.n; ++p) peers.a[p][(int64_t)i * ld + j] = v;
     }
+    POTF2_STAMP(14);
     // ---- inverse.  Step 1: off-diagonal 32-blocks of the two 64 x 64 halves, W_ba = -inv(L_b) (L_ba inv(L_a)).
     {
         const int half = warp >> 2, w4 = warp & 3;         // warps 0-3: blocks (1,0); warps 4-7: blocks (3,2)
@@ -469,12 +662,24 @@ __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double*
                         -1.0, false, 4, lane);
     }
     __syncthreads();
+    POTF2_STAMP(15);
     for (int e = tid; e < PT * PT; e += 256) {
         const int i = e >> 7, j = e & 127;
         const double v = (j <= i) ? sm[i * PLD + j] : 0.0;
         invd[e] = v;
         for (int p = 0; p < peers.n; ++p) peers.invd[p][e] = v;
     }
+    if (peers.n > 0) {  // publish: every thread's peer stores are fenced, then one thread per peer releases the flag
+        __threadfence_system();
+        __syncthreads();
+        if (tid < peers.n) asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(peers.flag[tid]), "l"(peers.val) : "memory");
+    }
+    POTF2_STAMP(16);
+}
+
+int set_potf2_debug(long long* dev_buf) {
+    PIGP_CUDA(cudaMemcpyToSymbol(g_potf2_dbg, &dev_buf, sizeof(dev_buf)));
+    return PIGP_OK;
 }
 
 int launch_potf2(double* A, int64_t ld, double* invd, int32_t* info, int base, const PeerTiles& peers, cudaStream_t st) {
@@ -710,6 +915,10 @@ int launch_gemv(const double* A, int64_t ld, int64_t m, int64_t n, const double*
 }
 
 int preload_dense() {
+    PIGP_CUDA(cudaFuncSetAttribute(k_gemm_s<32, 128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (32 + 128) * LDS_K * (int)sizeof(double)));
+    PIGP_CUDA(cudaFuncSetAttribute(k_gemm_s<64, 64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (64 + 64) * LDS_K * (int)sizeof(double)));
+    PIGP_PRELOAD((k_gemm_s<32, 128, 3>));
+    PIGP_PRELOAD((k_gemm_s<64, 64, 3>));
     PIGP_TRY((gemm_attrs<128, 4>()));
     PIGP_TRY((gemm_attrs<64, 3>()));
     PIGP_CUDA(cudaFuncSetAttribute(k_potf2, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM));

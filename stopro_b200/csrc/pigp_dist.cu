@@ -69,17 +69,14 @@ __global__ void __launch_bounds__(256) k_push_rows(const double* Y, int64_t ld, 
 
 // diagonal tile c of Y <- inv(L_cc)^T (full tile: zeros below the diagonal)
 __global__ void __launch_bounds__(256) k_place_diag_t(double* Y, int64_t ld, const double* invd, int first, int stride) {
-    const int c = first + blockIdx.x * stride;
+    const int c = first + (blockIdx.x >> 4) * stride;
     double* dst = Y + (int64_t)c * 128 * ld + (int64_t)c * 128;
     const double* src = invd + (int64_t)c * 128 * 128;
     __shared__ double sh[32][33];
-    for (int bt = 0; bt < 16; ++bt) {  // 32 x 32 sub-blocks
-        const int bi = bt >> 2, bj = bt & 3;
-        for (int e = threadIdx.x; e < 1024; e += 256) sh[e >> 5][e & 31] = src[(bi * 32 + (e >> 5)) * 128 + bj * 32 + (e & 31)];
-        __syncthreads();
-        for (int e = threadIdx.x; e < 1024; e += 256) dst[(int64_t)(bj * 32 + (e >> 5)) * ld + bi * 32 + (e & 31)] = sh[e & 31][e >> 5];
-        __syncthreads();
-    }
+    const int bi = (blockIdx.x >> 2) & 3, bj = blockIdx.x & 3;  // one 32 x 32 sub-block per CTA
+    for (int e = threadIdx.x; e < 1024; e += 256) sh[e >> 5][e & 31] = src[(bi * 32 + (e >> 5)) * 128 + bj * 32 + (e & 31)];
+    __syncthreads();
+    for (int e = threadIdx.x; e < 1024; e += 256) dst[(int64_t)(bj * 32 + (e >> 5)) * ld + bi * 32 + (e & 31)] = sh[e & 31][e >> 5];
 }
 
 // alpha[j] = sum_{k >= tile(j) * 128} Y[j][k] v[k]   (one warp per row; Y upper triangular by tiles)
@@ -158,6 +155,8 @@ __global__ void k_copy_v(const double* row, int64_t npad, double* v) {
 
 using namespace pigp;
 
+static bool g_side_stream = true;
+
 struct pigp_dsolver {
     pigp_plan* plan = nullptr;
     int rank = 0, world = 1;
@@ -174,6 +173,8 @@ struct pigp_dsolver {
     int n_flags = 0;
     char* peer_slab[8] = {};
     bool connected = false;
+    bool shared_device = false;  // a peer rank lives on this device (tests): flag waits stay in their own 1-CTA kernels,
+                                 // because a grid of spinning CTAs could starve the producer it is waiting for
     u64 epoch = 0;
     // private (not shared)
     AsmTile* d_tiles = nullptr;
@@ -181,6 +182,7 @@ struct pigp_dsolver {
     double *partials = nullptr, *gpart = nullptr, *out2 = nullptr, *v = nullptr, *alpha = nullptr;
     int32_t* info = nullptr;
     int* err = nullptr;
+    unsigned int* sig_counter = nullptr;  // arrival counter of the fused panel signal
     double *d_theta = nullptr, *d_y = nullptr, *d_res = nullptr, *h_res = nullptr;
     cudaStream_t own_stream = nullptr;  // the _host entry point runs here (ranks sharing a process must not share a stream)
     // internal streams: `sa` (high priority) carries the latency-bound Cholesky chain, `sb` the Y = L^-T products that
@@ -231,20 +233,20 @@ int signal(const Ctx& c, int idx) {
     return PIGP_OK;
 }
 
-int wait_one(const Ctx& c, int idx) {
+int wait_one(const Ctx& c, int idx, cudaStream_t st) {
     if (c.npeers == 0) return PIGP_OK;
-    ProfScope prof(PROF_MISC, c.st);
-    k_wait<<<1, 32, 0, c.st>>>(c.s->flags, idx, 0, 1, -1, c.s->epoch, c.s->err);
+    ProfScope prof(PROF_MISC, st);
+    k_wait<<<1, 32, 0, st>>>(c.s->flags, idx, 0, 1, -1, c.s->epoch, c.s->err);
     count_launch();
     PIGP_CUDA(cudaGetLastError());
     return PIGP_OK;
 }
 
 // flags[idx0 + src] for every src != rank
-int wait_all(const Ctx& c, int idx0) {
+int wait_all(const Ctx& c, int idx0, cudaStream_t st) {
     if (c.npeers == 0) return PIGP_OK;
-    ProfScope prof(PROF_MISC, c.st);
-    k_wait<<<1, 32, 0, c.st>>>(c.s->flags, idx0, 1, c.s->world, c.s->rank, c.s->epoch, c.s->err);
+    ProfScope prof(PROF_MISC, st);
+    k_wait<<<1, 32, 0, st>>>(c.s->flags, idx0, 1, c.s->world, c.s->rank, c.s->epoch, c.s->err);
     count_launch();
     PIGP_CUDA(cudaGetLastError());
     return PIGP_OK;
@@ -256,8 +258,26 @@ void set_push(const Ctx& c, GemmDesc& g, double* Cbase) {
     for (int k = 0; k < c.npeers; ++k) g.Cpeer[k] = c.s->peer(c.others[k], Cbase);
 }
 
+// wait for flag idx before GEMM g on stream st: fused into the GEMM prologue, or (ranks sharing a device) its own kernel
+int set_wait_one(const Ctx& c, GemmDesc& g, int idx, cudaStream_t st) {
+    if (c.npeers == 0) return PIGP_OK;
+    if (c.s->shared_device) return wait_one(c, idx, st);
+    g.wait_flags = c.s->flags; g.wait_idx0 = idx; g.wait_stride = 0; g.wait_count = 1; g.wait_skip = -1;
+    g.wait_val = c.s->epoch; g.wait_err = c.s->err;
+    return PIGP_OK;
+}
+int set_wait_all(const Ctx& c, GemmDesc& g, int idx0, cudaStream_t st) {
+    if (c.npeers == 0) return PIGP_OK;
+    if (c.s->shared_device) return wait_all(c, idx0, st);
+    g.wait_flags = c.s->flags; g.wait_idx0 = idx0; g.wait_stride = 1; g.wait_count = c.s->world; g.wait_skip = c.s->rank;
+    g.wait_val = c.s->epoch; g.wait_err = c.s->err;
+    return PIGP_OK;
+}
+
 // ---- merged recursion over column tiles [c0, c0 + nt): Cholesky on the chain stream; when the gradient is wanted,
-// the products of Y = L^-T that depend only on finished panels are issued on the side stream behind events.
+// the products of Y = L^-T that depend only on finished panels are issued on the side stream.  Flag waits are fused
+// into the prologue of the consuming GEMM and flag signals into the epilogue of the producing kernel wherever a kernel
+// exists to carry them; events order the side stream behind this rank's own producers.
 int leaf(const Ctx& c, int k) {
     pigp_dsolver* s = c.s;
     const int64_t ld = s->ld;
@@ -267,13 +287,15 @@ int leaf(const Ctx& c, int k) {
         double* Akk = s->L + (int64_t)k * TILE * ld + (int64_t)k * TILE;
         PeerTiles pt{};
         pt.n = c.npeers;
-        for (int q = 0; q < c.npeers; ++q) { pt.a[q] = s->peer(c.others[q], Akk); pt.invd[q] = s->peer(c.others[q], invk); }
+        pt.val = s->epoch;
+        for (int q = 0; q < c.npeers; ++q) {
+            pt.a[q] = s->peer(c.others[q], Akk);
+            pt.invd[q] = s->peer(c.others[q], invk);
+            pt.flag[q] = c.pf.f[q] + s->f_diag(k);
+        }
         PIGP_TRY(launch_potf2(Akk, ld, invk, s->info, k * TILE, pt, c.st));
-        PIGP_TRY(signal(c, s->f_diag(k)));
-    } else {
-        PIGP_TRY(wait_one(c, s->f_diag(k)));
     }
-    if (c.grad) PIGP_CUDA(cudaEventRecord(s->ev_diag[k], c.st));
+    if (c.grad) PIGP_CUDA(cudaEventRecord(s->ev_diag[k], c.st));  // mine: inv(L_kk) is ready; else: the chain has reached leaf k
     {
         // L_ik = A_ik inv(L_kk)^T for the own row tiles below (and the y tile), mirrored into every peer
         const int first = s->first_own(k + 1), cnt = s->count_own(k + 1, s->gy + 1);
@@ -288,16 +310,24 @@ int leaf(const Ctx& c, int k) {
             g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = k; g.k_gt0 = k;
             g.force_bn128 = 1;  // in place
             set_push(c, g, Cb);
+            if (!mine) PIGP_TRY(set_wait_one(c, g, s->f_diag(k), c.st));
+            if (c.npeers > 0) {
+                g.sig_counter = s->sig_counter; g.sig_total = cnt * (TILE / 32); g.sig_n = c.npeers; g.sig_val = s->epoch;
+                for (int q = 0; q < c.npeers; ++q) g.sig_flag[q] = c.pf.f[q] + s->f_panel(k, s->rank);
+            }
             PIGP_TRY(launch_gemm(g, c.st));
+        } else {
+            if (!mine) PIGP_TRY(wait_one(c, s->f_diag(k), c.st));
+            PIGP_TRY(signal(c, s->f_panel(k, s->rank)));
         }
-        PIGP_TRY(signal(c, s->f_panel(k, s->rank)));
     }
     if (c.grad) {
+        PIGP_CUDA(cudaEventRecord(s->ev_upd[k], c.st));  // this rank's rows of panel k are final
         // Y[j, k] = R[j, k] inv(L_kk)^T for own row tiles j < k; Y[k, k] = inv(L_kk)^T
         PIGP_CUDA(cudaStreamWaitEvent(c.sb, s->ev_diag[k], 0));
         if (mine) {
             ProfScope prof(PROF_MISC, c.sb);
-            k_place_diag_t<<<1, 256, 0, c.sb>>>(s->Y, ld, s->invd, k, 1);
+            k_place_diag_t<<<16, 256, 0, c.sb>>>(s->Y, ld, s->invd, k, 1);
             count_launch();
             PIGP_CUDA(cudaGetLastError());
         }
@@ -312,6 +342,7 @@ int leaf(const Ctx& c, int k) {
             g.C = Cb; g.ldc = ld;
             g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = k; g.k_gt0 = k;
             g.force_bn128 = 1;
+            if (!mine) PIGP_TRY(set_wait_one(c, g, s->f_diag(k), c.sb));
             PIGP_TRY(launch_gemm(g, c.sb));
         }
     }
@@ -324,8 +355,7 @@ int rec(const Ctx& c, int c0, int nt) {
     const int64_t ld = s->ld;
     const int n1 = nt / 2, n2 = nt - n1;
     PIGP_TRY(rec(c, c0, n1));
-    PIGP_TRY(wait_all(c, s->f_panel(c0 + n1 - 1, 0)));  // every peer's rows of the panels [c0, c0 + n1) have arrived
-    if (c.grad) PIGP_CUDA(cudaEventRecord(s->ev_upd[c0 + n1 - 1], c.st));
+    const int k1 = c0 + n1 - 1;  // once every peer's PANEL[k1] flag is up, all rows of the panels [c0, c0 + n1) have arrived
     {
         // trailing update of the own row tiles: C[i, J2] -= L[i, K1] L[J2, K1]^T (lower part)
         const int first = s->first_own(c0 + n1), cnt = s->count_own(c0 + n1, s->gy + 1);
@@ -338,12 +368,13 @@ int rec(const Ctx& c, int c0, int nt) {
             g.C = s->L + (int64_t)first * TILE * ld + (int64_t)(c0 + n1) * TILE; g.ldc = ld;
             g.lower_only = 1;
             g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = c0 + n1; g.k_gt0 = c0;
+            PIGP_TRY(set_wait_all(c, g, s->f_panel(k1, 0), c.st));
             PIGP_TRY(launch_gemm(g, c.st));
         }
     }
     if (c.grad) {
         // Y[j, J2] -= sum_{k in K1, k >= j} Y[j, k] L[J2, k]^T for the own row tiles j < c0 + n1
-        PIGP_CUDA(cudaStreamWaitEvent(c.sb, s->ev_upd[c0 + n1 - 1], 0));
+        PIGP_CUDA(cudaStreamWaitEvent(c.sb, s->ev_upd[k1], 0));
         const int first = s->first_own(0), cnt = s->count_own(0, c0 + n1);
         if (cnt > 0) {
             GemmDesc g{};
@@ -354,6 +385,7 @@ int rec(const Ctx& c, int c0, int nt) {
             g.C = s->Y + (int64_t)first * TILE * ld + (int64_t)(c0 + n1) * TILE; g.ldc = ld;
             g.kmode = 1;
             g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = c0 + n1; g.k_gt0 = c0;
+            PIGP_TRY(set_wait_all(c, g, s->f_panel(k1, 0), c.sb));
             PIGP_TRY(launch_gemm(g, c.sb));
         }
     }
@@ -376,7 +408,7 @@ extern "C" {
 void pigp_dsolver_destroy(pigp_dsolver* s) {
     if (!s) return;
     cudaFree(s->slab); cudaFree(s->d_tiles); cudaFree(s->partials); cudaFree(s->gpart); cudaFree(s->out2); cudaFree(s->v);
-    cudaFree(s->alpha); cudaFree(s->info); cudaFree(s->err); cudaFree(s->d_theta); cudaFree(s->d_y); cudaFree(s->d_res);
+    cudaFree(s->alpha); cudaFree(s->info); cudaFree(s->err); cudaFree(s->sig_counter); cudaFree(s->d_theta); cudaFree(s->d_y); cudaFree(s->d_res);
     if (s->h_res) cudaFreeHost(s->h_res);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     if (s->sa) cudaStreamDestroy(s->sa);
@@ -439,6 +471,8 @@ int pigp_dsolver_create(pigp_plan* plan, int rank, int world, pigp_dsolver** out
     cuda_ok(cudaMalloc(&s->info, sizeof(int32_t)), "cudaMalloc info");
     cuda_ok(cudaMalloc(&s->err, sizeof(int)), "cudaMalloc err");
     if (rc == PIGP_OK) cuda_ok(cudaMemset(s->err, 0, sizeof(int)), "memset err");
+    cuda_ok(cudaMalloc(&s->sig_counter, sizeof(unsigned int)), "cudaMalloc sig_counter");
+    if (rc == PIGP_OK) cuda_ok(cudaMemset(s->sig_counter, 0, sizeof(unsigned int)), "memset sig_counter");
     cuda_ok(cudaMalloc(&s->d_theta, sizeof(double) * MAX_THETA), "cudaMalloc theta");
     cuda_ok(cudaMalloc(&s->d_y, sizeof(double) * s->n), "cudaMalloc y");
     cuda_ok(cudaMalloc(&s->d_res, sizeof(double) * (1 + MAX_THETA)), "cudaMalloc res");
@@ -460,6 +494,11 @@ int pigp_dsolver_create(pigp_plan* plan, int rank, int world, pigp_dsolver** out
     if (rc != PIGP_OK) { pigp_dsolver_destroy(s); return rc; }
     s->connected = (world == 1);
     *out = s;
+    return PIGP_OK;
+}
+
+int pigp_set_side_stream(int on) {
+    g_side_stream = on != 0;
     return PIGP_OK;
 }
 
@@ -501,7 +540,9 @@ int pigp_dsolver_connect(pigp_dsolver* s, void* const* slabs) {
         if (!slabs[p]) { set_error("pigp_dsolver_connect: missing peer slab"); return PIGP_EINVAL; }
         s->peer_slab[p] = static_cast<char*>(slabs[p]);
         cudaPointerAttributes at{};
-        if (cudaPointerGetAttributes(&at, slabs[p]) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device != me) {
+        const bool known = cudaPointerGetAttributes(&at, slabs[p]) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+        if (known && at.device == me) s->shared_device = true;
+        if (known && at.device != me) {
             const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);  // same-process peers on another device
             if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
                 set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
@@ -524,7 +565,7 @@ int pigp_dsolver_nll_grad(pigp_dsolver* s, const double* theta_dev, const double
     const int64_t ld = s->ld;
     s->epoch += 1;
     Ctx c = make_ctx(s, st);
-    c.sb = s->sb;
+    c.sb = g_side_stream ? s->sb : st;  // serial mode (per-kernel timing): everything on the chain stream
     c.grad = grad_dev != nullptr;
     int32_t* info = s->info;
     PIGP_CUDA(cudaEventRecord(s->ev_in, user));
@@ -532,14 +573,14 @@ int pigp_dsolver_nll_grad(pigp_dsolver* s, const double* theta_dev, const double
     PIGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
     // every peer has finished reading what the previous call left in this rank's buffers
     PIGP_TRY(signal(c, s->f_bar(s->rank)));
-    PIGP_TRY(wait_all(c, s->f_bar(0)));
+    PIGP_TRY(wait_all(c, s->f_bar(0), st));
     const int first = s->first_own(0), cnt = s->count_own(0, s->T);
     if (c.grad) {
         PIGP_CUDA(cudaEventRecord(s->ev_bar, st));
-        PIGP_CUDA(cudaStreamWaitEvent(s->sb, s->ev_bar, 0));
+        PIGP_CUDA(cudaStreamWaitEvent(c.sb, s->ev_bar, 0));
         if (cnt > 0)
             PIGP_CUDA(cudaMemset2DAsync(s->Y + (int64_t)first * TILE * ld, sizeof(double) * TILE * ld * s->world, 0,
-                                        sizeof(double) * TILE * ld, cnt, s->sb));
+                                        sizeof(double) * TILE * ld, cnt, c.sb));
     }
     // own rows of K (lower, jitter added), identity padding (owner of the last tile), own y tile
     PIGP_TRY(launch_assemble(p, s->d_tiles, s->n_tiles, theta_dev, eps, 1, s->L, ld, st));
@@ -562,7 +603,7 @@ int pigp_dsolver_nll_grad(pigp_dsolver* s, const double* theta_dev, const double
     count_launch();
     PIGP_CUDA(cudaGetLastError());
     if (c.grad) {
-        PIGP_CUDA(cudaEventRecord(s->ev_b, s->sb));
+        PIGP_CUDA(cudaEventRecord(s->ev_b, c.sb));
         PIGP_CUDA(cudaStreamWaitEvent(st, s->ev_b, 0));  // own rows of Y are complete
         if (c.npeers > 0) {
             if (cnt > 0) {
@@ -575,7 +616,7 @@ int pigp_dsolver_nll_grad(pigp_dsolver* s, const double* theta_dev, const double
                 PIGP_CUDA(cudaGetLastError());
             }
             PIGP_TRY(signal(c, s->f_ydone(s->rank)));
-            PIGP_TRY(wait_all(c, s->f_ydone(0)));
+            PIGP_TRY(wait_all(c, s->f_ydone(0), st));
         }
         // alpha = K^-1 y = Y (L^-1 y), redundantly on every rank
         {
@@ -608,7 +649,7 @@ int pigp_dsolver_nll_grad(pigp_dsolver* s, const double* theta_dev, const double
         }
         PIGP_CUDA(cudaGetLastError());
         PIGP_TRY(signal(c, s->f_grad(s->rank)));
-        PIGP_TRY(wait_all(c, s->f_grad(0)));
+        PIGP_TRY(wait_all(c, s->f_grad(0), st));
         k_sum_slots<<<1, 32, 0, st>>>(s->gslots, s->world, p->theta_len, grad_dev, info, s->err);
         count_launch();
         PIGP_CUDA(cudaGetLastError());

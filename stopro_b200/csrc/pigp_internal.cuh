@@ -53,6 +53,7 @@ struct ProfScope {
         PIGP_CUDA(cudaFuncGetAttributes(&_a, f));              \
     } while (0)
 int preload_dense();
+int set_potf2_debug(long long* dev_buf);  // 17 clock64 stamps of the next k_potf2 launches (nullptr: off)
 int preload_assemble();
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
@@ -131,9 +132,23 @@ struct GemmDesc {
     int npeers;
     int push_gm_end;
     double* Cpeer[7];  // the address of C[0][0] in each peer's buffer (same ldc)
+    // ---- flag wait fused into the prologue: every CTA waits until flags[wait_idx0 + t * wait_stride] >= wait_val for
+    // t in [0, wait_count), t != wait_skip (bounded spin; *wait_err is set on time-out)
+    const unsigned long long* wait_flags;
+    int wait_idx0, wait_stride, wait_count, wait_skip;
+    unsigned long long wait_val;
+    int* wait_err;
+    // ---- flag signal fused into the epilogue: the last of sig_total CTAs stores sig_val to the sig_n peer flags
+    // (small-tile kernel only; sig_total must equal the number of CTAs that reach the epilogue)
+    unsigned int* sig_counter;
+    int sig_total, sig_n;
+    unsigned long long sig_val;
+    unsigned long long* sig_flag[7];
 };
 int launch_gemm(const GemmDesc& g, cudaStream_t st);
-struct PeerTiles { int n; double* a[7]; double* invd[7]; };  // peer addresses of the diagonal tile / its inverse
+struct PeerTiles {  // peer addresses of the diagonal tile / its inverse, and the epoch flag published after they are stored
+    int n; double* a[7]; double* invd[7]; unsigned long long* flag[7]; unsigned long long val;
+};
 int launch_potf2(double* A, int64_t ld, double* invd, int32_t* info, int base, const PeerTiles& peers, cudaStream_t st);
 int potrf_lower(double* A, int64_t ld, int64_t n, int64_t m_extra, double* invd, int32_t* info, cudaStream_t st);
 int potri_lower(const double* L, int64_t ld, int64_t n, const double* invd, double* W, double* X, cudaStream_t st);
