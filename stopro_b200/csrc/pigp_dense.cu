@@ -501,15 +501,17 @@ constexpr int PT = 128;
 constexpr int PLD = PT + 4;   // 132 = 4 mod 16: conflict-free DMMA fragment loads in both orientations
 constexpr int SLD = 36;       // 32 x 32 scratch blocks, same residue
 constexpr int N_SCRATCH = 6;  // inv(L_kk) x 4, two temporaries
-constexpr int POTF2_SMEM = (PT * PLD + N_SCRATCH * 32 * SLD) * (int)sizeof(double);
+constexpr int POTF2_SMEM = (PT * PLD + N_SCRATCH * 32 * SLD + 32 + 128) * (int)sizeof(double);
 
 // C(8 x 32 strip) = (accumulate ? C : 0) + alpha * sum_k A(row, k) * Bop(col, k);  Bop(col,k) = B_KN ? B[k][col] : B[col][k].
 // Pointers are pre-offset to the strip / operand origin.  n_tiles (1..4) of the four 8 x 8 column tiles are stored.
-template <bool B_KN>
-__device__ __forceinline__ void strip_mma(double* C, int ldc, const double* A, int lda, const double* B, int ldb, int K,
+// K is processed in chunks of 32 whose operands are fetched up front (40 shared loads in flight), and each 8 x 8 tile
+// accumulates in two independent chains, so a strip costs ~4 dependent DMMAs per 32 of K instead of 8 load-use steps.
+template <bool B_KN, int K>
+__device__ __forceinline__ void strip_mma(double* C, int ldc, const double* A, int lda, const double* B, int ldb,
                                           double alpha, bool accumulate, int n_tiles, int lane) {
     const int gid = lane >> 2, tig = lane & 3;
-    double acc[4][2];
+    double acc[4][2], acc2[4][2];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         if (accumulate && t < n_tiles) {
@@ -519,116 +521,170 @@ __device__ __forceinline__ void strip_mma(double* C, int ldc, const double* A, i
         } else {
             acc[t][0] = acc[t][1] = 0.0;
         }
+        acc2[t][0] = acc2[t][1] = 0.0;
     }
-    for (int k4 = 0; k4 < K; k4 += 4) {
-        const double a = alpha * A[gid * lda + k4 + tig];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const double b = B_KN ? B[(k4 + tig) * ldb + t * 8 + gid] : B[(t * 8 + gid) * ldb + k4 + tig];
-            dmma(acc[t][0], acc[t][1], a, b);
+    for (int kc = 0; kc < K; kc += 32) {
+        double a[8], b[8][4];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            a[q] = alpha * A[gid * lda + kc + 4 * q + tig];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                b[q][t] = B_KN ? B[(kc + 4 * q + tig) * ldb + t * 8 + gid] : B[(t * 8 + gid) * ldb + kc + 4 * q + tig];
         }
+#pragma unroll
+        for (int q = 0; q < 8; q += 2)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                dmma(acc[t][0], acc[t][1], a[q], b[q][t]);
+                dmma(acc2[t][0], acc2[t][1], a[q + 1], b[q + 1][t]);
+            }
     }
 #pragma unroll
     for (int t = 0; t < 4; ++t)
-        if (t < n_tiles) *reinterpret_cast<double2*>(C + gid * ldc + t * 8 + tig * 2) = make_double2(acc[t][0], acc[t][1]);
+        if (t < n_tiles)
+            *reinterpret_cast<double2*>(C + gid * ldc + t * 8 + tig * 2) = make_double2(acc[t][0] + acc2[t][0], acc[t][1] + acc2[t][1]);
 }
 
-// Warp-level Cholesky + inverse of the 32 x 32 block at D (row stride ld): lane i owns row i.
-// L overwrites the lower triangle of D (zeros above), inv(L) goes to Winv (row stride SLD, zeros above).
-__device__ __forceinline__ void warp_potrf32(double* D, int ld, double* Winv, int32_t* info, int base, int lane) {
+__device__ long long* g_potf2_dbg = nullptr;  // optional phase stamps (tools/potf2_bench.py)
+#define POTF2_STAMP(i) do { if (g_potf2_dbg && threadIdx.x == 0) g_potf2_dbg[i] = clock64(); } while (0)
+
+// Warp-level Cholesky + inverse of the 32 x 32 block at D (shared memory, row stride ld).
+// Factor: lane i owns row i in registers; per column one broadcast of the pivot, one rsqrt, and the rank-1 update with
+// the column exchanged by shuffles.  Every lane also tracks its own future pivot S[i][i] locally (piv -= L[i][j]^2), so
+// the pivot -> rsqrt -> scale -> pivot chain never waits for the column exchange.
+// Inverse: L goes back to shared memory, then lane c solves column c of W = inv(L) right-looking
+// (w_i = r_i / L_ii; r_m -= L[m][i] w_i), the factor's entries coming from broadcast shared loads.
+// L overwrites the lower triangle of D (zeros above); W goes to Winv (row stride SLD, zeros above).
+__device__ __forceinline__ void warp_potrf32(double* D, int ld, double* Winv, double* rdiag_sm, int32_t* info, int base, int lane) {
+    // rdiag_sm: 32 doubles for 1 / L_ii, followed by a double-buffered exchange area of 2 x 32 double2 (column, pivot)
+    double2* xch = reinterpret_cast<double2*>(rdiag_sm + 32);
     double a[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? D[lane * ld + c] : 0.0;
+    double piv = D[lane * ld + lane];
     double my_rdiag = 0.0;  // 1 / L[lane][lane]
+    xch[lane] = make_double2(0.0, piv);
+    __syncwarp();
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-        const double d = __shfl_sync(0xffffffffu, a[j], j);
+        // one exchange per column through shared memory (a warp shuffle of a double costs two SHFL plus a convergence
+        // barrier inside this warp-specialised branch): buffer j & 1 holds (L[i][j-1], pivot candidate S[i][i]) of lane i
+        const double d = xch[(j & 1) * 32 + j].y;
         if (lane == 0 && !(d > 0.0) && info) atomicCAS(info, 0, base + j + 1);
         const double rinv = rsqrt(d);  // NaN for d < 0, like the reference's jnp.linalg.cholesky
         const double aj = (lane > j) ? a[j] * rinv : ((lane == j) ? d * rinv : 0.0);
         a[j] = aj;
         if (lane == j) my_rdiag = rinv;
+        piv = fma(-aj, aj, piv);
+        double2* nxt = xch + ((j + 1) & 1) * 32;
+        nxt[lane] = make_double2(aj, piv);
+        __syncwarp();
 #pragma unroll
-        for (int k = j + 1; k < 32; ++k) {
-            const double lk = __shfl_sync(0xffffffffu, aj, k);  // L[k][j]
-            a[k] = fma(-aj, lk, a[k]);
-        }
+        for (int k = j + 1; k < 32; ++k) a[k] = fma(-aj, nxt[k].x, a[k]);  // L[k][j]: broadcast load
     }
+    POTF2_STAMP(13);
 #pragma unroll
     for (int c = 0; c < 32; ++c) D[lane * ld + c] = (c <= lane) ? a[c] : 0.0;
-    // inverse: lane j owns column j of W;  w[i] = (delta_ij - sum_{k<i} L[i][k] w[k]) / L[i][i]
-    double w[32];
+    rdiag_sm[lane] = my_rdiag;
+    __syncwarp();
+    double r[32];
+#pragma unroll
+    for (int m = 0; m < 32; ++m) r[m] = (m == lane) ? 1.0 : 0.0;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-        double s0 = 0.0, s1 = 0.0;
+        const double w = r[i] * rdiag_sm[i];
+        r[i] = w;
 #pragma unroll
-        for (int k = 0; k < i; ++k) {
-            const double lik = __shfl_sync(0xffffffffu, a[k], i);  // L[i][k] from the lane that owns row i
-            if (k & 1) s1 = fma(lik, w[k], s1);
-            else s0 = fma(lik, w[k], s0);
-        }
-        const double rd = __shfl_sync(0xffffffffu, my_rdiag, i);
-        const double rhs = (lane == i) ? 1.0 : 0.0;
-        w[i] = (lane <= i) ? (rhs - (s0 + s1)) * rd : 0.0;
+        for (int m = i + 1; m < 32; ++m) r[m] = fma(-D[m * ld + i], w, r[m]);
     }
+    POTF2_STAMP(14);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) Winv[i * SLD + lane] = w[i];
+    for (int i = 0; i < 32; ++i) Winv[i * SLD + lane] = r[i];
 }
 
 // Factor the lower triangle of the 128 x 128 tile at A in place (the upper part of the tile is set to zero) and write
 // inv(L) (lower, zeros above) to invd[128*128].  Non-positive pivot -> *info = base + column + 1 (first one wins)
 // and NaNs propagate, which is what jnp.linalg.cholesky gives the reference.
-__device__ long long* g_potf2_dbg = nullptr;  // optional phase stamps (tools/potf2_bench.py)
-#define POTF2_STAMP(i) do { if (g_potf2_dbg && threadIdx.x == 0) g_potf2_dbg[i] = clock64(); } while (0)
-
+// Peers (multi-GPU) receive inv(L) and the diagonal of L -- what their TRSMs and their log-det read -- then the flag.
 __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double* invd, int32_t* info, int base, PeerTiles peers) {
     extern __shared__ __align__(16) double sm[];
     double* scratch = sm + PT * PLD;
+    double* rdiag = scratch + N_SCRATCH * 32 * SLD;  // 32 doubles
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     POTF2_STAMP(0);
+    // tile -> shared memory (16-byte asynchronous copies, all in flight at once), then zero the strict upper triangle
+#pragma unroll 8
+    for (int c = tid; c < PT * PT / 2; c += 256) {
+        const int i = c >> 6, j2 = (c & 63) * 2;
+        cp_async16(sm + i * PLD + j2, A + (int64_t)i * ld + j2);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
     for (int e = tid; e < PT * PT; e += 256) {
         const int i = e >> 7, j = e & 127;
-        sm[i * PLD + j] = (j <= i) ? A[(int64_t)i * ld + j] : 0.0;
+        if (j > i) sm[i * PLD + j] = 0.0;
     }
     __syncthreads();
     POTF2_STAMP(1);
-    for (int kb = 0; kb < 4; ++kb) {
+    // kb = -1: factor block 0; kb >= 0: panel kb, then the trailing update of which warp 0 takes the next diagonal block
+    // (strips 0-3 of column group 0) and factors it at once while warps 1-7 update the rest.  (One call site of
+    // warp_potrf32: its straight-line code is ~60 KB and a second copy would thrash the instruction cache.)
+    for (int kb = -1; kb < 3; ++kb) {
         const int o = 32 * kb;
-        double* invk = scratch + kb * 32 * SLD;
-        if (warp == 0) warp_potrf32(sm + o * PLD + o, PLD, invk, info, base + o, lane);
-        __syncthreads();
-        POTF2_STAMP(2 + 3 * kb);
         const int r_lo = o + 32;
         const int n_strips = (PT - r_lo) / 8;
-        // panel: rows below the block, L_ik = A_ik inv(L_kk)^T, in place (a strip is read entirely before it is written)
-        for (int st = warp; st < n_strips; st += 8) {
-            double* X = sm + (r_lo + st * 8) * PLD + o;
-            strip_mma<false>(X, PLD, X, PLD, invk, SLD, 32, 1.0, false, 4, lane);
+        if (kb >= 0) {
+            // panel: rows below the block, L_ik = A_ik inv(L_kk)^T, in place (a strip is read entirely before it is written)
+            const double* invk = scratch + kb * 32 * SLD;
+            for (int st = warp; st < n_strips; st += 8) {
+                double* X = sm + (r_lo + st * 8) * PLD + o;
+                strip_mma<false, 32>(X, PLD, X, PLD, invk, SLD, 1.0, false, 4, lane);
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        POTF2_STAMP(3 + 3 * kb);
-        // trailing update (lower): tasks = (8-row strip, 32-column group at or left of it)
-        int task = 0;
-        for (int st = 0; st < n_strips; ++st) {
-            const int n_groups = st / 4 + 1;
-            for (int cg = 0; cg < n_groups; ++cg, ++task) {
-                if ((task & 7) != warp) continue;
-                const int r0 = r_lo + st * 8, c0 = r_lo + cg * 32;
-                const int n_tiles = min(4, (r0 - c0) / 8 + 1);  // tiles at or left of the diagonal tile
-                strip_mma<false>(sm + r0 * PLD + c0, PLD, sm + r0 * PLD + o, PLD, sm + c0 * PLD + o, PLD, 32, -1.0, true,
-                                 n_tiles, lane);
+        POTF2_STAMP(3 + 2 * kb);
+        if (warp == 0) {
+            if (kb >= 0) {
+                for (int st = 0; st < 4; ++st)
+                    strip_mma<false, 32>(sm + (r_lo + st * 8) * PLD + r_lo, PLD, sm + (r_lo + st * 8) * PLD + o, PLD,
+                                         sm + r_lo * PLD + o, PLD, -1.0, true, st + 1, lane);
+                __syncwarp();
+            }
+            warp_potrf32(sm + r_lo * PLD + r_lo, PLD, scratch + (kb + 1) * 32 * SLD, rdiag, info, base + r_lo, lane);
+        } else if (kb >= 0) {
+            // trailing update (lower): tasks = (8-row strip, 32-column group at or left of it)
+            int task = 0;
+            for (int st = 4; st < n_strips; ++st) {
+                const int n_groups = st / 4 + 1;
+                for (int cg = 0; cg < n_groups; ++cg, ++task) {
+                    if (task % 7 != warp - 1) continue;
+                    const int r0 = r_lo + st * 8, c0 = r_lo + cg * 32;
+                    const int n_tiles = min(4, (r0 - c0) / 8 + 1);  // tiles at or left of the diagonal tile
+                    strip_mma<false, 32>(sm + r0 * PLD + c0, PLD, sm + r0 * PLD + o, PLD, sm + c0 * PLD + o, PLD, -1.0, true,
+                                         n_tiles, lane);
+                }
             }
         }
         __syncthreads();
-        POTF2_STAMP(4 + 3 * kb);
+        POTF2_STAMP(4 + 2 * kb);
     }
-    for (int e = tid; e < PT * PT; e += 256) {
-        const int i = e >> 7, j = e & 127;
-        const double v = (j <= i) ? sm[i * PLD + j] : 0.0;
-        A[(int64_t)i * ld + j] = v;
-        for (int p = 0; p < peers.n; ++p) peers.a[p][(int64_t)i * ld + j] = v;
+    POTF2_STAMP(9);
+    // L -> global (16-byte stores); peers get the diagonal only
+    for (int c = tid; c < PT * PT / 2; c += 256) {
+        const int i = c >> 6, j2 = (c & 63) * 2;
+        double2 v;
+        v.x = (j2 <= i) ? sm[i * PLD + j2] : 0.0;
+        v.y = (j2 + 1 <= i) ? sm[i * PLD + j2 + 1] : 0.0;
+        *reinterpret_cast<double2*>(A + (int64_t)i * ld + j2) = v;
     }
-    POTF2_STAMP(14);
+    if (tid < PT) {
+        const double v = sm[tid * PLD + tid];
+        for (int p = 0; p < peers.n; ++p) peers.a[p][(int64_t)tid * ld + tid] = v;
+    }
+    POTF2_STAMP(10);
     // ---- inverse.  Step 1: off-diagonal 32-blocks of the two 64 x 64 halves, W_ba = -inv(L_b) (L_ba inv(L_a)).
     {
         const int half = warp >> 2, w4 = warp & 3;         // warps 0-3: blocks (1,0); warps 4-7: blocks (3,2)
@@ -637,9 +693,9 @@ __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double*
         const double* invb = scratch + (2 * half + 1) * 32 * SLD;
         double* tmp = scratch + (4 + half) * 32 * SLD;
         double* Lba = sm + rb * PLD + ra;
-        strip_mma<true>(tmp + w4 * 8 * SLD, SLD, Lba + w4 * 8 * PLD, PLD, inva, SLD, 32, 1.0, false, 4, lane);
+        strip_mma<true, 32>(tmp + w4 * 8 * SLD, SLD, Lba + w4 * 8 * PLD, PLD, inva, SLD, 1.0, false, 4, lane);
         __syncthreads();
-        strip_mma<true>(Lba + w4 * 8 * PLD, PLD, invb + w4 * 8 * SLD, SLD, tmp, SLD, 32, -1.0, false, 4, lane);
+        strip_mma<true, 32>(Lba + w4 * 8 * PLD, PLD, invb + w4 * 8 * SLD, SLD, tmp, SLD, -1.0, false, 4, lane);
     }
     __syncthreads();
     // Step 2: diagonal 32-blocks <- inv(L_kk) (full blocks, zeros above the diagonal)
@@ -651,30 +707,33 @@ __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double*
     // Step 3: T = L21 W11 into the upper-right quadrant; 16 tasks (8 strips x 2 column groups)
     for (int task = warp; task < 16; task += 8) {
         const int st = task >> 1, cg = task & 1;
-        strip_mma<true>(sm + (st * 8) * PLD + 64 + cg * 32, PLD, sm + (64 + st * 8) * PLD, PLD, sm + cg * 32, PLD, 64, 1.0,
-                        false, 4, lane);
+        strip_mma<true, 64>(sm + (st * 8) * PLD + 64 + cg * 32, PLD, sm + (64 + st * 8) * PLD, PLD, sm + cg * 32, PLD, 1.0,
+                            false, 4, lane);
     }
     __syncthreads();
     // Step 4: W21 = -W22 T
     for (int task = warp; task < 16; task += 8) {
         const int st = task >> 1, cg = task & 1;
-        strip_mma<true>(sm + (64 + st * 8) * PLD + cg * 32, PLD, sm + (64 + st * 8) * PLD + 64, PLD, sm + 64 + cg * 32, PLD, 64,
-                        -1.0, false, 4, lane);
+        strip_mma<true, 64>(sm + (64 + st * 8) * PLD + cg * 32, PLD, sm + (64 + st * 8) * PLD + 64, PLD, sm + 64 + cg * 32, PLD,
+                            -1.0, false, 4, lane);
     }
     __syncthreads();
-    POTF2_STAMP(15);
-    for (int e = tid; e < PT * PT; e += 256) {
-        const int i = e >> 7, j = e & 127;
-        const double v = (j <= i) ? sm[i * PLD + j] : 0.0;
-        invd[e] = v;
-        for (int p = 0; p < peers.n; ++p) peers.invd[p][e] = v;
+    POTF2_STAMP(11);
+    for (int c = tid; c < PT * PT / 2; c += 256) {
+        const int i = c >> 6, j2 = (c & 63) * 2;
+        double2 v;
+        v.x = (j2 <= i) ? sm[i * PLD + j2] : 0.0;
+        v.y = (j2 + 1 <= i) ? sm[i * PLD + j2 + 1] : 0.0;
+        *reinterpret_cast<double2*>(invd + i * PT + j2) = v;
+        if (j2 <= i)
+            for (int p = 0; p < peers.n; ++p) *reinterpret_cast<double2*>(peers.invd[p] + i * PT + j2) = v;
     }
     if (peers.n > 0) {  // publish: every thread's peer stores are fenced, then one thread per peer releases the flag
         __threadfence_system();
         __syncthreads();
         if (tid < peers.n) asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(peers.flag[tid]), "l"(peers.val) : "memory");
     }
-    POTF2_STAMP(16);
+    POTF2_STAMP(12);
 }
 
 int set_potf2_debug(long long* dev_buf) {

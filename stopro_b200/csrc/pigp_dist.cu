@@ -452,8 +452,9 @@ int pigp_dsolver_create(pigp_plan* plan, int rank, int world, pigp_dsolver** out
         s->invd = reinterpret_cast<double*>(p); p += i_bytes;
         s->gslots = reinterpret_cast<double*>(p); p += (g_bytes + 255) / 256 * 256;
         s->flags = reinterpret_cast<u64*>(p);
-        cuda_ok(cudaMemset(s->flags, 0, f_bytes), "memset flags");
-        cuda_ok(cudaMemset(s->gslots, 0, g_bytes), "memset gslots");
+        // zero everything once: flags and slots start at epoch 0, and the upper triangles of the inverse diagonal tiles
+        // (never written on peers) must read as zero
+        cuda_ok(cudaMemset(s->slab, 0, s->slab_bytes), "memset slab");
         s->peer_slab[rank] = s->slab;
     }
     std::vector<AsmTile> tiles;
