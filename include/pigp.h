@@ -165,6 +165,11 @@ int pigp_dsolver_ipc_handle(const pigp_dsolver* s, void* handle64);
 int pigp_ipc_open(const void* handle64, void** ptr);
 int pigp_ipc_close(void* ptr);
 int pigp_dsolver_connect(pigp_dsolver* s, void* const* slabs /* world pointers; entry [rank] is ignored */);
+/* Whether another rank computes on the same physical GPU (tests).  _connect detects it for peers of the same process;
+ * with CUDA IPC the caller compares pigp_device_uuid() across ranks and says so.  Ranks that share a GPU wait for flags
+ * in separate one-CTA kernels instead of inside the consuming GEMMs (spinning grids could starve their producer). */
+int pigp_dsolver_set_shared_device(pigp_dsolver* s, int shared);
+int pigp_device_uuid(void* out16);
 /* trainingFunction_all + d_trainingFunction_all (GP/gp.py:213-224, :412-488) over the sharded K.  grad_dev may be NULL
  * (NLL only).  Asynchronous on `stream`. */
 int pigp_dsolver_nll_grad(pigp_dsolver* s, const double* theta_dev, const double* y_dev, double eps, double* nll_dev,

@@ -73,6 +73,8 @@ _SIGNATURES = {
     "pigp_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "pigp_ipc_close": (C.c_int, [C.c_void_p]),
     "pigp_dsolver_connect": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pigp_dsolver_set_shared_device": (C.c_int, [C.c_void_p, C.c_int]),
+    "pigp_device_uuid": (C.c_int, [C.c_void_p]),
     "pigp_dsolver_nll_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p]),
     "pigp_dsolver_nll_grad_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p,

@@ -67,6 +67,52 @@ __global__ void __launch_bounds__(256) k_push_rows(const double* Y, int64_t ld, 
     }
 }
 
+// Publication to the peers by dedicated multi-CTA kernels on their own stream, off the Cholesky chain: coalesced 16-byte
+// stores over NVLink; the last CTA to finish (system-scope fence, arrival counter) releases the epoch flag on every peer.
+struct PushSig { unsigned int* counter; int idx; u64 val; int n; u64* flag[8]; };  // peers' flag arrays and this rank's own
+__device__ __forceinline__ void push_done(const PushSig& sg) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(sg.counter, 1u);
+        if (done == gridDim.x - 1) {
+            *sg.counter = 0u;
+            __threadfence_system();
+            for (int p = 0; p < sg.n; ++p)
+                asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(sg.flag[p] + sg.idx), "l"(sg.val) : "memory");
+        }
+    }
+}
+// rows of the own tiles first, first + stride, ... (count tiles) x columns [col0, col0 + 128) of L; 4 CTAs per tile
+__global__ void __launch_bounds__(256) k_push_panel(const double* L, int64_t ld, int64_t col0, int first, int stride, PeerBufs pb, PushSig sg) {
+    const int tile = first + (blockIdx.x >> 2) * stride;
+    const int64_t row0 = (int64_t)tile * 128 + (blockIdx.x & 3) * 32;
+    for (int e = threadIdx.x; e < 32 * 64; e += 256) {
+        const int64_t off = (row0 + (e >> 6)) * ld + col0 + (e & 63) * 2;
+        const double2 v = *reinterpret_cast<const double2*>(L + off);
+        for (int p = 0; p < pb.n; ++p) *reinterpret_cast<double2*>(pb.p[p] + off) = v;
+    }
+    push_done(sg);
+}
+// inverse diagonal tile (lower triangle) and the diagonal of L_kk (all the peers read of it: the log-det); 8 CTAs
+struct PeerDiag { int n; double* invd[7]; double* lkk[7]; };
+__global__ void __launch_bounds__(256) k_push_diag(const double* invk, const double* Lkk, int64_t ld, PeerDiag pd, PushSig sg) {
+    const int r0 = blockIdx.x * 16;
+    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+        const int i = r0 + (e >> 6), j2 = (e & 63) * 2;
+        if (j2 <= i) {
+            const double2 v = *reinterpret_cast<const double2*>(invk + i * 128 + j2);
+            for (int p = 0; p < pd.n; ++p) *reinterpret_cast<double2*>(pd.invd[p] + i * 128 + j2) = v;
+        }
+    }
+    if (threadIdx.x < 16) {
+        const int i = r0 + threadIdx.x;
+        const double v = Lkk[(int64_t)i * ld + i];
+        for (int p = 0; p < pd.n; ++p) pd.lkk[p][(int64_t)i * ld + i] = v;
+    }
+    push_done(sg);
+}
+
 // diagonal tile c of Y <- inv(L_cc)^T (full tile: zeros below the diagonal)
 __global__ void __launch_bounds__(256) k_place_diag_t(double* Y, int64_t ld, const double* invd, int first, int stride) {
     const int c = first + (blockIdx.x >> 4) * stride;
@@ -187,8 +233,8 @@ struct pigp_dsolver {
     cudaStream_t own_stream = nullptr;  // the _host entry point runs here (ranks sharing a process must not share a stream)
     // internal streams: `sa` (high priority) carries the latency-bound Cholesky chain, `sb` the Y = L^-T products that
     // depend only on finished panels, so that they fill the bubbles of the chain
-    cudaStream_t sa = nullptr, sb = nullptr;
-    cudaEvent_t ev_in = nullptr, ev_bar = nullptr, ev_b = nullptr, ev_out = nullptr;
+    cudaStream_t sa = nullptr, sb = nullptr, sc = nullptr;  // sc: publication kernels (peer stores), off the chain
+    cudaEvent_t ev_in = nullptr, ev_bar = nullptr, ev_b = nullptr, ev_c = nullptr, ev_out = nullptr;
     std::vector<cudaEvent_t> ev_diag, ev_upd;
 
     int f_diag(int k) const { return k; }
@@ -208,6 +254,7 @@ struct Ctx {
     pigp_dsolver* s;
     cudaStream_t st;   // chain stream
     cudaStream_t sb;   // side stream (Y = L^-T), used when grad is set
+    cudaStream_t sc;   // publication stream
     bool grad;
     PeerFlags pf;
     int npeers;
@@ -278,26 +325,36 @@ int set_wait_all(const Ctx& c, GemmDesc& g, int idx0, cudaStream_t st) {
 // the products of Y = L^-T that depend only on finished panels are issued on the side stream.  Flag waits are fused
 // into the prologue of the consuming GEMM and flag signals into the epilogue of the producing kernel wherever a kernel
 // exists to carry them; events order the side stream behind this rank's own producers.
+PushSig make_sig(const Ctx& c, int idx) {
+    PushSig sg{};
+    sg.counter = c.s->sig_counter + 1; sg.idx = idx; sg.val = c.s->epoch;
+    for (int q = 0; q < c.npeers; ++q) sg.flag[q] = c.pf.f[q];
+    sg.flag[c.npeers] = c.s->flags;
+    sg.n = c.npeers + 1;
+    return sg;
+}
+
 int leaf(const Ctx& c, int k) {
     pigp_dsolver* s = c.s;
     const int64_t ld = s->ld;
     double* invk = s->invd + (int64_t)k * TILE * TILE;
-    const bool mine = (k % s->world == s->rank);
-    if (mine) {
-        double* Akk = s->L + (int64_t)k * TILE * ld + (int64_t)k * TILE;
-        PeerTiles pt{};
-        pt.n = c.npeers;
-        pt.val = s->epoch;
-        for (int q = 0; q < c.npeers; ++q) {
-            pt.a[q] = s->peer(c.others[q], Akk);
-            pt.invd[q] = s->peer(c.others[q], invk);
-            pt.flag[q] = c.pf.f[q] + s->f_diag(k);
-        }
-        PIGP_TRY(launch_potf2(Akk, ld, invk, s->info, k * TILE, pt, c.st));
+    double* Akk = s->L + (int64_t)k * TILE * ld + (int64_t)k * TILE;
+    const bool mine = (k % s->world == s->rank), multi = c.npeers > 0;
+    if (mine) PIGP_TRY(launch_potf2(Akk, ld, invk, s->info, k * TILE, PeerTiles{}, c.st));
+    if (c.grad || multi) PIGP_CUDA(cudaEventRecord(s->ev_diag[k], c.st));  // mine: inv(L_kk) is ready; else: the chain has reached leaf k
+    if (mine && multi) {
+        // publish inv(L_kk) and diag(L_kk) from the publication stream while the chain goes on with this rank's own TRSM
+        PIGP_CUDA(cudaStreamWaitEvent(c.sc, s->ev_diag[k], 0));
+        PeerDiag pd{};
+        pd.n = c.npeers;
+        for (int q = 0; q < c.npeers; ++q) { pd.invd[q] = s->peer(c.others[q], invk); pd.lkk[q] = s->peer(c.others[q], Akk); }
+        ProfScope prof(PROF_MISC, c.sc);
+        k_push_diag<<<8, 256, 0, c.sc>>>(invk, Akk, ld, pd, make_sig(c, s->f_diag(k)));
+        count_launch();
+        PIGP_CUDA(cudaGetLastError());
     }
-    if (c.grad) PIGP_CUDA(cudaEventRecord(s->ev_diag[k], c.st));  // mine: inv(L_kk) is ready; else: the chain has reached leaf k
     {
-        // L_ik = A_ik inv(L_kk)^T for the own row tiles below (and the y tile), mirrored into every peer
+        // L_ik = A_ik inv(L_kk)^T for the own row tiles below (and the y tile)
         const int first = s->first_own(k + 1), cnt = s->count_own(k + 1, s->gy + 1);
         if (cnt > 0) {
             GemmDesc g{};
@@ -309,20 +366,28 @@ int leaf(const Ctx& c, int k) {
             g.C = Cb; g.ldc = ld;
             g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = k; g.k_gt0 = k;
             g.force_bn128 = 1;  // in place
-            set_push(c, g, Cb);
             if (!mine) PIGP_TRY(set_wait_one(c, g, s->f_diag(k), c.st));
-            if (c.npeers > 0) {
-                g.sig_counter = s->sig_counter; g.sig_total = cnt * (TILE / 32); g.sig_n = c.npeers; g.sig_val = s->epoch;
-                for (int q = 0; q < c.npeers; ++q) g.sig_flag[q] = c.pf.f[q] + s->f_panel(k, s->rank);
-            }
             PIGP_TRY(launch_gemm(g, c.st));
-        } else {
-            if (!mine) PIGP_TRY(wait_one(c, s->f_diag(k), c.st));
-            PIGP_TRY(signal(c, s->f_panel(k, s->rank)));
+        }
+        if (c.grad || multi) PIGP_CUDA(cudaEventRecord(s->ev_upd[k], c.st));  // this rank's rows of panel k are final
+        if (multi) {
+            // publish them (rows of the matrix proper; the y tile is private) and raise PANEL[k][rank] on every peer
+            PIGP_CUDA(cudaStreamWaitEvent(c.sc, s->ev_upd[k], 0));
+            const int pcnt = s->count_own(k + 1, s->T);
+            ProfScope prof(PROF_MISC, c.sc);
+            if (pcnt > 0) {
+                PeerBufs pb{};
+                pb.n = c.npeers;
+                for (int q = 0; q < c.npeers; ++q) pb.p[q] = s->peer(c.others[q], s->L);
+                k_push_panel<<<pcnt * 4, 256, 0, c.sc>>>(s->L, ld, (int64_t)k * TILE, first, s->world, pb, make_sig(c, s->f_panel(k, s->rank)));
+            } else {
+                k_signal<<<1, 32, 0, c.sc>>>(c.pf, s->f_panel(k, s->rank), s->epoch);
+            }
+            count_launch();
+            PIGP_CUDA(cudaGetLastError());
         }
     }
     if (c.grad) {
-        PIGP_CUDA(cudaEventRecord(s->ev_upd[k], c.st));  // this rank's rows of panel k are final
         // Y[j, k] = R[j, k] inv(L_kk)^T for own row tiles j < k; Y[k, k] = inv(L_kk)^T
         PIGP_CUDA(cudaStreamWaitEvent(c.sb, s->ev_diag[k], 0));
         if (mine) {
@@ -397,7 +462,7 @@ int preload_dist() {
     PIGP_TRY(preload_assemble());
     PIGP_PRELOAD(k_signal); PIGP_PRELOAD(k_wait); PIGP_PRELOAD(k_push_rows); PIGP_PRELOAD(k_place_diag_t);
     PIGP_PRELOAD(k_gemv_upper); PIGP_PRELOAD(k_set_ytile); PIGP_PRELOAD(k_push_vec); PIGP_PRELOAD(k_sum_slots);
-    PIGP_PRELOAD(k_finish_nll_d); PIGP_PRELOAD(k_diag_info); PIGP_PRELOAD(k_copy_v);
+    PIGP_PRELOAD(k_finish_nll_d); PIGP_PRELOAD(k_diag_info); PIGP_PRELOAD(k_copy_v); PIGP_PRELOAD(k_push_panel); PIGP_PRELOAD(k_push_diag);
     return PIGP_OK;
 }
 
@@ -413,7 +478,8 @@ void pigp_dsolver_destroy(pigp_dsolver* s) {
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     if (s->sa) cudaStreamDestroy(s->sa);
     if (s->sb) cudaStreamDestroy(s->sb);
-    for (cudaEvent_t e : {s->ev_in, s->ev_bar, s->ev_b, s->ev_out}) if (e) cudaEventDestroy(e);
+    if (s->sc) cudaStreamDestroy(s->sc);
+    for (cudaEvent_t e : {s->ev_in, s->ev_bar, s->ev_b, s->ev_c, s->ev_out}) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : s->ev_diag) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : s->ev_upd) if (e) cudaEventDestroy(e);
     delete s;
@@ -472,8 +538,8 @@ int pigp_dsolver_create(pigp_plan* plan, int rank, int world, pigp_dsolver** out
     cuda_ok(cudaMalloc(&s->info, sizeof(int32_t)), "cudaMalloc info");
     cuda_ok(cudaMalloc(&s->err, sizeof(int)), "cudaMalloc err");
     if (rc == PIGP_OK) cuda_ok(cudaMemset(s->err, 0, sizeof(int)), "memset err");
-    cuda_ok(cudaMalloc(&s->sig_counter, sizeof(unsigned int)), "cudaMalloc sig_counter");
-    if (rc == PIGP_OK) cuda_ok(cudaMemset(s->sig_counter, 0, sizeof(unsigned int)), "memset sig_counter");
+    cuda_ok(cudaMalloc(&s->sig_counter, 2 * sizeof(unsigned int)), "cudaMalloc sig_counter");
+    if (rc == PIGP_OK) cuda_ok(cudaMemset(s->sig_counter, 0, 2 * sizeof(unsigned int)), "memset sig_counter");
     cuda_ok(cudaMalloc(&s->d_theta, sizeof(double) * MAX_THETA), "cudaMalloc theta");
     cuda_ok(cudaMalloc(&s->d_y, sizeof(double) * s->n), "cudaMalloc y");
     cuda_ok(cudaMalloc(&s->d_res, sizeof(double) * (1 + MAX_THETA)), "cudaMalloc res");
@@ -484,7 +550,8 @@ int pigp_dsolver_create(pigp_plan* plan, int rank, int world, pigp_dsolver** out
         cuda_ok(cudaDeviceGetStreamPriorityRange(&lo, &hi), "cudaDeviceGetStreamPriorityRange");
         cuda_ok(cudaStreamCreateWithPriority(&s->sa, cudaStreamNonBlocking, hi), "cudaStreamCreate sa");
         cuda_ok(cudaStreamCreateWithPriority(&s->sb, cudaStreamNonBlocking, lo), "cudaStreamCreate sb");
-        for (cudaEvent_t* e : {&s->ev_in, &s->ev_bar, &s->ev_b, &s->ev_out}) cuda_ok(cudaEventCreateWithFlags(e, cudaEventDisableTiming), "cudaEventCreate");
+        cuda_ok(cudaStreamCreateWithPriority(&s->sc, cudaStreamNonBlocking, hi), "cudaStreamCreate sc");
+        for (cudaEvent_t* e : {&s->ev_in, &s->ev_bar, &s->ev_b, &s->ev_c, &s->ev_out}) cuda_ok(cudaEventCreateWithFlags(e, cudaEventDisableTiming), "cudaEventCreate");
         s->ev_diag.assign(s->T, nullptr);
         s->ev_upd.assign(s->T, nullptr);
         for (int k = 0; k < s->T; ++k) {
@@ -556,6 +623,22 @@ int pigp_dsolver_connect(pigp_dsolver* s, void* const* slabs) {
     return PIGP_OK;
 }
 
+int pigp_dsolver_set_shared_device(pigp_dsolver* s, int shared) {
+    if (!s) { set_error("pigp_dsolver_set_shared_device: null solver"); return PIGP_EINVAL; }
+    s->shared_device = shared != 0;
+    return PIGP_OK;
+}
+
+int pigp_device_uuid(void* out16) {
+    if (!out16) { set_error("pigp_device_uuid: null argument"); return PIGP_EINVAL; }
+    int dev = 0;
+    PIGP_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    PIGP_CUDA(cudaGetDeviceProperties(&prop, dev));
+    std::memcpy(out16, &prop.uuid, 16);
+    return PIGP_OK;
+}
+
 int pigp_dsolver_nll_grad(pigp_dsolver* s, const double* theta_dev, const double* y_dev, double eps, double* nll_dev,
                           double* grad_dev, int32_t* info_dev, void* stream) {
     if (!s || !theta_dev || !y_dev || !nll_dev) { set_error("pigp_dsolver_nll_grad: null argument"); return PIGP_EINVAL; }
@@ -567,6 +650,7 @@ int pigp_dsolver_nll_grad(pigp_dsolver* s, const double* theta_dev, const double
     s->epoch += 1;
     Ctx c = make_ctx(s, st);
     c.sb = g_side_stream ? s->sb : st;  // serial mode (per-kernel timing): everything on the chain stream
+    c.sc = g_side_stream ? s->sc : st;
     c.grad = grad_dev != nullptr;
     int32_t* info = s->info;
     PIGP_CUDA(cudaEventRecord(s->ev_in, user));
@@ -595,6 +679,17 @@ int pigp_dsolver_nll_grad(pigp_dsolver* s, const double* theta_dev, const double
     }
     PIGP_CUDA(cudaGetLastError());
     PIGP_TRY(rec(c, 0, s->T));
+    if (c.npeers > 0) {
+        // the diagonal of every L_kk (log-det) travels with the DIAG flags; a GEMM only waits for the flags it consumes
+        ProfScope prof(PROF_MISC, st);
+        for (int k0 = 0; k0 < s->T; k0 += 32) {
+            k_wait<<<1, 32, 0, st>>>(s->flags, s->f_diag(k0), 1, std::min(32, s->T - k0), -1, s->epoch, s->err);
+            count_launch();
+        }
+        PIGP_CUDA(cudaGetLastError());
+        PIGP_CUDA(cudaEventRecord(s->ev_c, c.sc));
+        PIGP_CUDA(cudaStreamWaitEvent(st, s->ev_c, 0));
+    }
     // every rank holds all of L now (the panel flags of every peer were awaited inside rec for all but the final leaf,
     // whose diagonal tile arrives with its DIAG flag)
     PIGP_TRY(launch_logdet_quad(s->L, ld, s->n, ytile, s->out2, st));

@@ -95,7 +95,12 @@ class DistSolver:
         """One process per GPU: exchange CUDA-IPC handles over torch.distributed and map every peer's slab."""
         if self.world == 1:
             return
-        handles = exchange_handles(self.ipc_handle(), group)
+        uuid = (C.c_char * 16)()
+        _lib.check(_lib.lib().pigp_device_uuid(uuid))
+        mine = bytes(uuid)
+        both = exchange_handles(self.ipc_handle() + mine, group)
+        handles = [b[:_lib.IPC_HANDLE_BYTES] for b in both]
+        shared = any(b[_lib.IPC_HANDLE_BYTES:] == mine for r, b in enumerate(both) if r != self.rank)
         slabs = []
         for r, hb in enumerate(handles):
             if r == self.rank:
@@ -106,6 +111,7 @@ class DistSolver:
             self._opened.append(ptr.value)
             slabs.append(ptr.value)
         self.connect_pointers(slabs)
+        _lib.check(_lib.lib().pigp_dsolver_set_shared_device(self.handle, int(shared)))
 
     # -- evaluation
     def nll_grad(self, theta_ptr, y_ptr, eps, nll_ptr, grad_ptr, info_ptr=None, stream=None):
