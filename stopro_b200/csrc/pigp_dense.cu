@@ -94,7 +94,7 @@ __device__ __forceinline__ void load_frags(double2* frag, const double* sm, int 
 // Bounded spin on epoch flags written by peers (st.release.sys); see pigp_dist.cu.
 __device__ __forceinline__ void wait_flags(const GemmDesc& g, int tid) {
     if (g.wait_count <= 0) return;
-    if (tid < g.wait_count && tid != g.wait_skip) {
+    if (tid < g.wait_count && tid != g.wait_skip && *reinterpret_cast<volatile int*>(g.wait_err) == 0) {
         const unsigned long long* p = g.wait_flags + g.wait_idx0 + (int64_t)tid * g.wait_stride;
         unsigned long long t0, now, v;
         asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t0));

@@ -17,6 +17,7 @@
 //   * log-det, |L^-1 y|^2 and alpha = K^-1 y are computed redundantly from the replicated L / Y; each rank carries its
 //     own y row tile (placed at the first tile index >= npad/128 that it owns) through the TRSMs.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "pigp_internal.cuh"
@@ -41,6 +42,7 @@ __global__ void k_wait(const u64* flags, int idx0, int stride, int count, int sk
     const int t = threadIdx.x;
     if (t >= count || t == skip) return;
     const u64* p = flags + idx0 + (int64_t)t * stride;
+    if (*reinterpret_cast<volatile int*>(err) != 0) return;  // a wait already timed out in this solver: fail fast
     u64 t0 = 0, now = 0;
     asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t0));
     for (;;) {
@@ -202,6 +204,13 @@ __global__ void k_copy_v(const double* row, int64_t npad, double* v) {
 using namespace pigp;
 
 static bool g_side_stream = true;
+// Flag waits inside the prologue of the consuming GEMM save one tiny kernel per wait, but a grid of spinning CTAs can
+// keep this rank's own publication kernels (which a peer's progress depends on) off the SMs: off unless PIGP_FUSE_WAITS=1.
+static int g_fuse_waits = -1;
+static bool fuse_waits() {
+    if (g_fuse_waits < 0) { const char* e = getenv("PIGP_FUSE_WAITS"); g_fuse_waits = (e && atoi(e) == 1) ? 1 : 0; }
+    return g_fuse_waits == 1;
+}
 
 struct pigp_dsolver {
     pigp_plan* plan = nullptr;
@@ -308,14 +317,14 @@ void set_push(const Ctx& c, GemmDesc& g, double* Cbase) {
 // wait for flag idx before GEMM g on stream st: fused into the GEMM prologue, or (ranks sharing a device) its own kernel
 int set_wait_one(const Ctx& c, GemmDesc& g, int idx, cudaStream_t st) {
     if (c.npeers == 0) return PIGP_OK;
-    if (c.s->shared_device) return wait_one(c, idx, st);
+    if (c.s->shared_device || !fuse_waits()) return wait_one(c, idx, st);
     g.wait_flags = c.s->flags; g.wait_idx0 = idx; g.wait_stride = 0; g.wait_count = 1; g.wait_skip = -1;
     g.wait_val = c.s->epoch; g.wait_err = c.s->err;
     return PIGP_OK;
 }
 int set_wait_all(const Ctx& c, GemmDesc& g, int idx0, cudaStream_t st) {
     if (c.npeers == 0) return PIGP_OK;
-    if (c.s->shared_device) return wait_all(c, idx0, st);
+    return wait_all(c, idx0, st);  // never fused: the consumers are full-GPU grids (see fuse_waits)
     g.wait_flags = c.s->flags; g.wait_idx0 = idx0; g.wait_stride = 1; g.wait_count = c.s->world; g.wait_skip = c.s->rank;
     g.wait_val = c.s->epoch; g.wait_err = c.s->err;
     return PIGP_OK;
