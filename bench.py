@@ -26,7 +26,17 @@ sys.path.insert(0, ROOT)
 
 METRIC = "NLL+grad evals/s at N=20k"
 UNIT = "evals/s"
+NCU_TRAFFIC_BYTES = 26.54e9  # profiles/r01_v2_gemm_full_summary.txt
 FP64_PEAK_FALLBACK = 36.45  # TFLOP/s, cuBLAS DGEMM 16384^3 on this pool's B200 (profiles/r01_fp64_peak.json)
+
+
+def hbm_peak():
+    """Measured copy bandwidth of this pool's B200 (driver-written MEASURED_PEAKS.json), else the profiling guide's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "B200_PROFILING.md fallback"
 
 
 def parse():
@@ -285,7 +295,12 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "pigp::k_gemm (mma.sync.m8n8k4.f64 / DMMA.8x8x4)",
+                     "traffic": NCU_TRAFFIC_BYTES if world == 1 else None,
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the largest k_gemm launch of a step "
+                                     "(K^-1 = Y Y^T, 78.8 ms, N^3/3 flops) from profiles/r01_v2_gemm_full_summary.txt; "
+                                     "that launch reads 8x its algorithmic 3.2 GB but uses 4 % of HBM bandwidth "
+                                     "(FP64 tensor pipe 94 % busy)",
+                     "kernel": "pigp::k_gemm / k_gemm_s (mma.sync.m8n8k4.f64 / DMMA.8x8x4)",
                      "peak_source": peak_src,
                      "algorithmic_flops_per_step": algorithmic_flops,
                      "executed_tflops": gemm["flops"] / (gemm["ms"] * 1e-3) * 1e-12,
@@ -293,6 +308,11 @@ def run_ours(args):
                      "share_of_step": gemm["ms"] / step_ms_prof, "serial_step_ms": serial_ms,
                      "classes_ms": {k: round(v["ms"], 3) for k, v in prof.items()}},
         "nll": float(res[0]),
+        # secondary figure named by BASELINE.json's metric: the assembly kernel writes this rank's rows of the lower
+        # triangle of K (algorithmic bytes 8 N (N + 1) / 2 / n_gpus); it is bound by FP64 arithmetic (one exp and
+        # ~150 flops per entry of the 4th-derivative blocks), not by HBM
+        "assembly": {"ms": prof["assemble"]["ms"], "gb_per_s": 8.0 * N * (N + 1) / 2 / world / (prof["assemble"]["ms"] * 1e-3) * 1e-9,
+                     "hbm_peak_gb_per_s": hbm_peak()[0], "peak_source": hbm_peak()[1]},
     }
     if world == 1 and not args.no_cpu_baseline:
         v, sec = cpu_reference_eval(args.cpu_sample_n, N)
