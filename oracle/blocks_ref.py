@@ -154,6 +154,100 @@ TABLES = {
 }
 TABLES["sinusoidal_infer_gov"]["training"] = TABLES["sinusoidal"]["training"]
 
+# ---- the other live classes of the reference, restated name by name
+# GP/gp_sinusoidal_infer_difp.py:9-41 adds these methods to the 2-D library
+BLOCKS_2D_INFER_DIFP = dict(BLOCKS_2D)
+BLOCKS_2D_INFER_DIFP.update({
+    "Kpux": "0", "Kpuy": "0", "Kpfx": "+d10:pp", "Kpfy": "+d11:pp", "Kpdiv": "0",
+    "Kdifpux": "X(Kpux)", "Kdifpuy": "X(Kpuy)", "Kdifpfx": "X(Kpfx)", "Kdifpfy": "X(Kpfy)", "Kdifpdiv": "X(Kpdiv)",
+    "Kdifpdifux": "XX(Kpux)", "Kdifpdifuy": "XX(Kpuy)",
+})
+_SIN7 = _rows("""
+    Kuxux Kuxuy Kuxdifux Kuxdifuy Kuxfx Kuxfy Kuxdiv
+    Kuyuy Kuydifux Kuydifuy Kuyfx Kuyfy Kuydiv
+    Kdifuxdifux Kdifuxdifuy Kdifuxfx Kdifuxfy Kdifuxdiv
+    Kdifuydifuy Kdifuyfx Kdifuyfy Kdifuydiv
+    Kfxfx Kfxfy Kfxdiv
+    Kfyfy Kfydiv
+    Kdivdiv""")  # gp_sinusoidal_infer_difp.py:44-59
+TABLES.update({
+    "sinusoidal_infer_difp": {  # GPSinusoidalInferDifP :60-68
+        "dim": 2, "blocks": BLOCKS_2D_INFER_DIFP, "groups": GROUPS_2D, "training": _SIN7,
+        "mixed": _rows("Kdifpux Kdifpuy Kdifpdifux Kdifpdifuy Kdifpfx Kdifpfy Kdifpdiv"),
+        "test": _rows("Kdifpdifp"),
+    },
+    "sinusoidal_infer_u_without_difp": {  # GPSinusoidalInferUWithoutDifP :71-82
+        "dim": 2, "blocks": BLOCKS_2D, "groups": GROUPS_2D, "training": _SIN7,
+        "mixed": _rows("""
+            Kuxux Kuxuy Kuxdifux Kuxdifuy Kuxfx Kuxfy Kuxdiv
+            Kuyux Kuyuy Kuydifux Kuydifuy Kuyfx Kuyfy Kuydiv"""),
+        "test": _rows("""
+            Kuxux Kuxuy
+            Kuyuy"""),
+    },
+    "sinusoidal_infer_gov_without_difp": {  # GPSinusoidalInferGovWithoutDifP :85-101 (Kfxuy in the (fx, fy) test slot: :97)
+        "dim": 2, "blocks": BLOCKS_2D, "groups": GROUPS_2D, "training": _SIN7,
+        "mixed": _rows("""
+            Kfxux Kfxuy Kfxdifux Kfxdifuy Kfxfx Kfxfy Kfxdiv
+            Kfyux Kfyuy Kfydifux Kfydifuy Kfyfx Kfyfy Kfydiv
+            Kdivux Kdivuy Kdivdifux Kdivdifuy Kdivfx Kdivfy Kdivdiv"""),
+        "test": _rows("""
+            Kfxfx Kfxuy Kfxdiv
+            Kfyfy Kfydiv
+            Kdivdiv"""),
+    },
+    "stokes3d_infer_difp": {  # GPStokes3D(infer_difp=True): gp_stokes_3D.py:112-123, :163-166
+        "dim": 3, "blocks": BLOCKS_3D, "groups": GROUPS_3D, "training": TABLES["stokes3d"]["training"],
+        "mixed": _rows("Kdifpux Kdifpuy Kdifpuz Kdifpfx Kdifpfy Kdifpfz Kdifpdiv"),
+        "test": _rows("Kdifpdifp"),
+    },
+    "stokes3d_naive": {  # GPStokes3DNaive: gp_stokes_3D_naive.py:49-128
+        "dim": 3, "blocks": BLOCKS_3D, "groups": GROUPS_3D,
+        "training": _rows("""
+            Kuxux Kuxuy Kuxuz
+            Kuyuy Kuyuz
+            Kuzuz"""),
+        "mixed": _rows("""
+            Kuxux Kuxuy Kuxuz
+            Kuxuy Kuyuy Kuyuz
+            Kuxuz Kuyuz Kuzuz"""),
+        "test": TABLES["stokes3d"]["test"],
+    },
+    "stokes2d2c": {  # GPStokes2D2C: gp_stokes_3D_2D2C.py:14-78
+        "dim": 3, "blocks": BLOCKS_3D, "groups": GROUPS_3D,
+        "training": _rows("""
+            Kuxux Kuxuy Kuxfx Kuxfy Kuxfz Kuxdiv
+            Kuyuy Kuyfx Kuyfy Kuyfz Kuydiv
+            Kfxfx Kfxfy Kfxfz Kfxdiv
+            Kfyfy Kfyfz Kfydiv
+            Kfzfz Kfzdiv
+            Kdivdiv"""),
+        "mixed": _rows("""
+            Kuxux Kuxuy Kuxfx Kuxfy Kuxfz Kuxdiv
+            Kuxuy Kuyuy Kuyfx Kuyfy Kuyfz Kuydiv
+            Kuxuz Kuyuz Kuzfx Kuzfy Kuzfz Kuzdiv"""),
+        "test": TABLES["stokes3d"]["test"],
+    },
+    "stokes2d2c_surface": {  # GPStokes2D2CSurface: gp_stokes_3D_2D2C.py:86-188
+        "dim": 3, "blocks": BLOCKS_3D, "groups": GROUPS_3D,
+        "training": _rows("""
+            Kuxux Kuxuy Kuxux Kuxuy Kuxuz Kuxfx Kuxfy Kuxfz Kuxdiv
+            Kuyuy Kuyux Kuyuy Kuyuz Kuyfx Kuyfy Kuyfz Kuydiv
+            Kuxux Kuxuy Kuxuz Kuxfx Kuxfy Kuxfz Kuxdiv
+            Kuyuy Kuyuz Kuyfx Kuyfy Kuyfz Kuydiv
+            Kuzuz Kuzfx Kuzfy Kuzfz Kuzdiv
+            Kfxfx Kfxfy Kfxfz Kfxdiv
+            Kfyfy Kfyfz Kfydiv
+            Kfzfz Kfzdiv
+            Kdivdiv"""),
+        "mixed": _rows("""
+            Kuxux Kuxuy Kuxux Kuxuy Kuxuz Kuxfx Kuxfy Kuxfz Kuxdiv
+            Kuyux Kuyuy Kuyux Kuyuy Kuyuz Kuyfx Kuyfy Kuyfz Kuydiv
+            Kuxuz Kuyuz Kuxuz Kuyuz Kuzuz Kuzfx Kuzfy Kuzfz Kuzdiv"""),
+        "test": TABLES["stokes3d"]["test"],
+    },
+})
+
 
 def parse_spec(spec, blocks):
     """-> (terms, shift) with terms = [(sign, op, group)], shift in {None,'Xp','X','XX'}."""

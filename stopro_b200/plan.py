@@ -30,7 +30,7 @@ class Plan:
     """A block matrix  [cov(A_i(r_i), B_j(r'_j))]_{ij}  bound to its point sets."""
 
     def __init__(self, dim, product_form, fields, row_obs, row_pts, col_obs=None, col_pts=None, lbox=None,
-                 noise_blocks=None):
+                 noise_blocks=None, zero_blocks=()):
         self.dim, self.product_form, self.fields = dim, bool(product_form), list(fields)
         self.symmetric = col_obs is None
         self.row_obs, self.col_obs = list(row_obs), (list(row_obs) if col_obs is None else list(col_obs))
@@ -47,6 +47,8 @@ class Plan:
             for j in range(nc):
                 if self.symmetric and j < i:
                     continue
+                if (i, j) in zero_blocks:
+                    continue  # zero-initialised descriptor: n_terms = 0, the reference's Kzero
                 table[i * nc + j] = operators.make_desc(self.row_obs[i], self.col_obs[j], self.fields, dim,
                                                         self.product_form)
         self._table = table

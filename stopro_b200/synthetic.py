@@ -119,6 +119,56 @@ def drag3d(n_u=6, n_f=8, n_test=40, radius_cut=0.43):
                  np.tile([0.0, -1.0, -1.0, -1.0], 4))
 
 
+def sinusoidal_without_difp(variant="infer_difp", **kw):
+    """The sinusoidal channel trained without the pressure-difference block (GP/gp_sinusoidal_infer_difp.py):
+    variant in {"infer_difp", "infer_u_without_difp", "infer_gov_without_difp"}."""
+    base = sinusoidal(**kw)
+    r_train, f_train = base["r_train"][:7], base["f_train"][:7]
+    r_t = base["r_test"][0]
+    if variant == "infer_difp":
+        r_test = [base["r_train"][7]]          # inlet column: p(r + lbox) - p(r)
+        f_test = [np.full(len(r_test[0]), -30.0)]
+    elif variant == "infer_u_without_difp":
+        r_test, f_test = [r_t, r_t.copy()], [np.zeros(len(r_t)), np.zeros(len(r_t))]
+    else:
+        r_test = [r_t, r_t.copy(), r_t.copy()]
+        f_test = [np.full(len(r_t), 12.0), np.zeros(len(r_t)), np.zeros(len(r_t))]
+    return _pack("sinusoidal_" + variant, "sinusoidal_" + variant, dict(base["model_kwargs"], use_difp=False), base["kernel"],
+                 r_train, f_train, r_test, f_test, base["theta0"])
+
+
+def drag3d_variant(variant="stokes3d_naive", n_u=4, n_f=5, n_test=10):
+    """The 3-D sphere-drag data arranged for the other live 3-D classes: "stokes3d_naive" (velocity only,
+    GP/gp_stokes_3D_naive.py), "stokes2d2c" / "stokes2d2c_surface" (GP/gp_stokes_3D_2D2C.py) and
+    "stokes3d_infer_difp" (GPStokes3D(infer_difp=True), GP/gp_stokes_3D.py:112-123)."""
+    base = drag3d(n_u=n_u, n_f=n_f, n_test=n_test)
+    r_u, r_f = base["r_train"][0], base["r_train"][3]
+    ux, uy, uz = base["f_train"][:3]
+    zf = np.zeros(len(r_f))
+    kw = {}
+    r_test, f_test = base["r_test"], base["f_test"]
+    if variant == "stokes3d_naive":
+        r_train, f_train = [r_u, r_u.copy(), r_u.copy()], [ux, uy, uz]
+    elif variant == "stokes2d2c":
+        r_train = [r_u, r_u.copy(), r_f, r_f.copy(), r_f.copy(), r_f.copy()]
+        f_train = [ux, uy, zf, zf.copy(), zf.copy(), zf.copy()]
+    elif variant == "stokes2d2c_surface":
+        r_s = r_u[np.abs(r_u[:, 2]) > 0.9]      # "surface" points carrying all three components
+        sx, sy, sz = _stokes_sphere(r_s)
+        r_train = [r_u, r_u.copy(), r_s, r_s.copy(), r_s.copy(), r_f, r_f.copy(), r_f.copy(), r_f.copy()]
+        f_train = [ux, uy, sx, sy, sz, zf, zf.copy(), zf.copy(), zf.copy()]
+    elif variant == "stokes3d_infer_difp":
+        r_train, f_train = base["r_train"], base["f_train"]
+        kw = dict(lbox=np.array([1.94, 0.0, 0.0]), infer_difp=True)
+        g = np.linspace(-0.9, 0.9, 5)
+        yy, zz = np.meshgrid(g, g)
+        r_in = np.stack([np.full(25, -0.97), yy.reshape(-1), zz.reshape(-1)], 1)
+        r_test, f_test = [r_in], [np.zeros(25)]
+    else:
+        raise ValueError(variant)
+    return _pack(variant, variant, kw, base["kernel"], r_train, f_train, r_test, f_test, base["theta0"])
+
+
 def stokes2d_scaling(n_total=20000, seed=0, well_conditioned=True, n_test=1024):
     """C5: Poiseuille block structure [ux, uy, p, fx, fy, div] with fractions [.05, .05, .05, .2833, .2833, .2834],
     i.i.d. U[0,1]^2 points, product SE.  well_conditioned ties every length scale to the point spacing
@@ -147,6 +197,17 @@ def make_model(cfg):
     from .GP.gp_sinusoidal_independent import GPSinusoidalWithoutPIndependent
     from .GP.gp_stokes_3D import GPStokes3D
 
+    from .GP.gp_sinusoidal_infer_difp import (GPSinusoidalInferDifP, GPSinusoidalInferGovWithoutDifP,
+                                              GPSinusoidalInferUWithoutDifP)
+    from .GP.gp_stokes_3D_2D2C import GPStokes2D2C, GPStokes2D2CSurface
+    from .GP.gp_stokes_3D_naive import GPStokes3DNaive
+
     cls = dict(naive=GPmodelNaive, laplacian1d=GPmodel1DLaplacian, poiseuille=GPPoiseuilleIndependent,
-               sinusoidal=GPSinusoidalWithoutPIndependent, stokes3d=GPStokes3D)[cfg["model"]]
+               sinusoidal=GPSinusoidalWithoutPIndependent, stokes3d=GPStokes3D,
+               sinusoidal_infer_gov=GPSinusoidalWithoutPIndependent,
+               sinusoidal_infer_difp=GPSinusoidalInferDifP,
+               sinusoidal_infer_u_without_difp=GPSinusoidalInferUWithoutDifP,
+               sinusoidal_infer_gov_without_difp=GPSinusoidalInferGovWithoutDifP,
+               stokes3d_infer_difp=GPStokes3D, stokes3d_naive=GPStokes3DNaive, stokes2d2c=GPStokes2D2C,
+               stokes2d2c_surface=GPStokes2D2CSurface)[cfg["model"]]
     return cls(Kernel=define_kernel(cfg["kernel"]), **cfg["model_kwargs"])

@@ -25,7 +25,29 @@ CONFIGS = {
     "poiseuille_additive_eps1e-2": lambda: dict(synthetic.poiseuille(kernel_form="additive"), eps=1e-2),
     "poiseuille_product_eps1e-2": lambda: dict(synthetic.poiseuille(kernel_form="product"), eps=1e-2),
     "sinusoidal_eps1e-2": lambda: dict(synthetic.sinusoidal(u_num=16, f_nx=14, f_ny=8, dif_num=9, n_test=10), eps=1e-2),
+    # the other live classes of the reference, through the same descriptor compiler
+    "sinusoidal_infer_gov": lambda: dict(synthetic.sinusoidal(u_num=12, f_nx=10, f_ny=6, dif_num=7, n_test=8), eps=1e-2,
+                                         model="sinusoidal_infer_gov",
+                                         model_kwargs=dict(lbox=np.array([2.5, 0.0]), use_difp=True, use_difu=True,
+                                                           infer_governing_eqs=True),
+                                         **_gov_test(8)),
+    "sinusoidal_infer_difp": lambda: dict(synthetic.sinusoidal_without_difp("infer_difp", u_num=12, f_nx=10, f_ny=6, dif_num=7, n_test=8), eps=1e-2),
+    "sinusoidal_infer_u_without_difp": lambda: dict(synthetic.sinusoidal_without_difp("infer_u_without_difp", u_num=12, f_nx=10, f_ny=6, dif_num=7, n_test=8), eps=1e-2),
+    "sinusoidal_infer_gov_without_difp": lambda: dict(synthetic.sinusoidal_without_difp("infer_gov_without_difp", u_num=12, f_nx=10, f_ny=6, dif_num=7, n_test=8), eps=1e-2),
+    "stokes3d_infer_difp": lambda: dict(synthetic.drag3d_variant("stokes3d_infer_difp"), eps=1e-2),
+    "stokes3d_naive": lambda: dict(synthetic.drag3d_variant("stokes3d_naive"), eps=1e-2),
+    "stokes2d2c": lambda: dict(synthetic.drag3d_variant("stokes2d2c"), eps=1e-2),
+    "stokes2d2c_surface": lambda: dict(synthetic.drag3d_variant("stokes2d2c_surface"), eps=1e-2),
 }
+
+
+def _gov_test(n_test):
+    """test arrays for infer_governing_eqs: three blocks [fx, fy, div] on the sinusoidal test points"""
+    base = synthetic.sinusoidal(u_num=12, f_nx=10, f_ny=6, dif_num=7, n_test=n_test)
+    r_t = base["r_test"][0]
+    return dict(r_test=[r_t, r_t.copy(), r_t.copy()], mu_test=[np.zeros(len(r_t))] * 3,
+                f_test=[np.full(len(r_t), 12.0), np.zeros(len(r_t)), np.zeros(len(r_t))])
+
 STRICT = {"sin1d_naive", "sin1d_laplacian", "drag3d", "poiseuille_additive_eps1e-2", "poiseuille_product_eps1e-2",
           "sinusoidal_eps1e-2"}
 U = 2.0 ** -52
