@@ -30,6 +30,11 @@ NCU_TRAFFIC_BYTES = 26.54e9  # profiles/r01_v2_gemm_full_summary.txt
 FP64_PEAK_FALLBACK = 36.45  # TFLOP/s, cuBLAS DGEMM 16384^3 on this pool's B200 (profiles/r01_fp64_peak.json)
 
 
+def workload_name(n, p, eps):
+    return (f"C5 synthetic 2-D Stokes PIGP (blocks ux,uy,p,fx,fy,div), N={n}, P={p}, product SE, eps={eps}, "
+            "logl=log(4/sqrt(N))")
+
+
 def hbm_peak():
     """Measured copy bandwidth of this pool's B200 (driver-written MEASURED_PEAKS.json), else the profiling guide's fallback."""
     try:
@@ -95,10 +100,11 @@ def run_reference(args):
               f"({sec:.2f} s each), scaled to N={args.n} by (N/Ns)^3")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * sec * scale, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * sec * scale, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C5 synthetic 2-D Stokes PIGP, N={args.n}, P=9, product SE (timed on a bounded sample)",
-                   "sample_wall_s": wall},
+        "config": {"workload": workload_name(args.n, 9, 1e-6),
+                   "parallelism": f"CPU: restated reference algorithm (oracle/, numpy + LAPACK) on {cores} host cores, rank 0 only",
+                   "sample": sample, "sample_wall_s": wall},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -283,8 +289,7 @@ def run_ours(args):
         "metric": METRIC, "value": args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C5 synthetic 2-D Stokes PIGP (blocks ux,uy,p,fx,fy,div), N={N}, P={P}, product SE, "
-                               f"eps={eps}, logl=log(4/sqrt(N))",
+        "config": {"workload": workload_name(N, P, eps),
                    "parallelism": "single GPU" if world == 1 else
                    f"K dealt block-cyclically (128-row tiles) over {world} GPUs, one cooperative evaluation per step; "
                    "NVLink peer stores + flags, no library collective",

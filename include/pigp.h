@@ -191,6 +191,10 @@ int pigp_set_side_stream(int on);
 int pigp_profile_start(void);
 int pigp_profile_stop(double* ms_out, int64_t* launches_out, double* flops_out);
 
+/* Debug aid of tools/potf2_bench.py: when dev_buf != NULL the following k_potf2 launches write 17 clock64 phase
+ * stamps (thread 0) to it. */
+int pigp_debug_potf2_stamps(long long* dev_buf);
+
 #ifdef __cplusplus
 }
 #endif

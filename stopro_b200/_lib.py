@@ -81,6 +81,7 @@ _SIGNATURES = {
                                              C.c_void_p]),
     "pigp_launch_count": (C.c_int64, []),
     "pigp_set_side_stream": (C.c_int, [C.c_int]),
+    "pigp_debug_potf2_stamps": (C.c_int, [C.c_void_p]),
     "pigp_profile_start": (C.c_int, []),
     "pigp_profile_stop": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
 }

@@ -9,7 +9,6 @@ import torch
 from stopro_b200 import _lib
 
 lib = _lib.lib()
-lib.pigp_debug_potf2_stamps.argtypes = [C.c_void_p]
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 X = torch.randn(128, 512, dtype=torch.float64, device=dev)
