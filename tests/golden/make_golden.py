@@ -24,6 +24,11 @@ CASES = {
     "drag3d": lambda: dict(synthetic.drag3d(n_u=3, n_f=4, n_test=5), eps=1e-4),
     "sin1d_naive": lambda: synthetic.sin_1d_naive(n=16, n_test=11),
     "sin1d_laplacian": lambda: synthetic.sin_1d_laplacian(ly_num=10, n_test=11),
+    # other live classes of the reference
+    "sinusoidal_infer_difp": lambda: dict(synthetic.sinusoidal_without_difp("infer_difp", u_num=5, f_nx=5, f_ny=4, dif_num=4, n_test=4), eps=1e-4),
+    "sinusoidal_infer_gov_without_difp": lambda: dict(synthetic.sinusoidal_without_difp("infer_gov_without_difp", u_num=5, f_nx=5, f_ny=4, dif_num=4, n_test=3), eps=1e-4),
+    "stokes3d_infer_difp": lambda: dict(synthetic.drag3d_variant("stokes3d_infer_difp", n_u=3, n_f=3, n_test=4), eps=1e-4),
+    "stokes2d2c_surface": lambda: dict(synthetic.drag3d_variant("stokes2d2c_surface", n_u=3, n_f=3, n_test=4), eps=1e-3),
 }
 
 
@@ -38,6 +43,8 @@ def theta_of(cfg, seed=7):
 def main():
     out_dir = os.path.dirname(os.path.abspath(__file__))
     for name, make in CASES.items():
+        if "--only-missing" in sys.argv and os.path.exists(os.path.join(out_dir, f"{name}.npz")):
+            continue
         cfg = make()
         gp = oracle_for(cfg, backend="autodiff")
         th = theta_of(cfg)

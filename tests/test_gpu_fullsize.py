@@ -1,0 +1,62 @@
+"""GPU tests at BASELINE.json's full size (N = 20000 synthetic 2-D Stokes points, the bench workload), where the CPU
+oracle is too slow: size-independent properties of the path instead of entry-wise comparison.
+
+  * NLL(c y) is an exact quadratic in c (0.5 c^2 y^T K^-1 y + log-det + const): f(2) - 4 f(1) + 3 f(0) = 0
+    checks the triangular solves against the log-det path;
+  * the fused dK/dtheta trace gradient equals central finite differences of the NLL (factorisation, K^-1 and the
+    closed-form theta-derivatives all enter);
+  * the block-cyclic evaluation on 2 ranks gives the single-rank result, bitwise identical on both ranks.
+eps = 1 keeps cond(K) * u below 1e-8, so these are sharp (see tests/test_gpu_dist.py).
+"""
+import numpy as np
+import pytest
+
+from stopro_b200 import synthetic
+from test_gpu_dist import run_ranks
+
+pytestmark = pytest.mark.gpu
+N = 20000
+
+
+@pytest.fixture(scope="module")
+def problem(cuda_device):
+    cfg = dict(synthetic.stokes2d_scaling(N, n_test=8), eps=1.0)
+    gp = synthetic.make_model(cfg)
+    gp.set_constants(cfg["r_train"], cfg["delta_y"], cfg["eps"], only_training=True)
+    solver = gp._solver_for(cfg["r_train"])
+    th = cfg["theta0"] + 0.05 * np.random.default_rng(11).standard_normal(len(cfg["theta0"]))
+    nll, grad, info = solver.nll_grad_host(th, cfg["delta_y"], cfg["eps"])
+    assert info == 0 and np.isfinite(nll) and np.all(np.isfinite(grad))
+    yield cfg, gp, solver, th, nll, grad
+    gp.close()
+
+
+def test_nll_is_quadratic_in_y(problem):
+    cfg, gp, solver, th, nll, _ = problem
+    y, eps = cfg["delta_y"], cfg["eps"]
+    f = [solver.nll_grad_host(th, c * y, eps, want_grad=False)[0] for c in (0.0, 1.0, 2.0)]
+    assert f[1] == pytest.approx(nll, rel=1e-13)
+    quad = 2.0 * (f[1] - f[0])                      # y^T K^-1 y
+    assert quad > 0.0
+    assert abs(f[2] - 4.0 * f[1] + 3.0 * f[0]) <= 1e-10 * max(abs(f[1]), abs(quad))
+
+
+def test_gradient_matches_finite_differences(problem):
+    cfg, gp, solver, th, _, grad = problem
+    y, eps, h = cfg["delta_y"], cfg["eps"], 1e-4
+    scale = np.max(np.abs(grad))
+    for p in (0, 4, 8):                              # log gamma_ux, log l_x of uy, log l_y of p
+        e = np.zeros_like(th)
+        e[p] = h
+        fp = solver.nll_grad_host(th + e, y, eps, want_grad=False)[0]
+        fm = solver.nll_grad_host(th - e, y, eps, want_grad=False)[0]
+        assert abs((fp - fm) / (2.0 * h) - grad[p]) <= 1e-5 * scale, p
+
+
+def test_two_ranks_reproduce_the_single_rank_result(problem):
+    cfg, gp, _, th, nll, grad = problem
+    out = run_ranks(gp, cfg, th, 2)
+    assert out[0][2] == 0
+    assert abs(out[0][0] - nll) <= 1e-10 * abs(nll)
+    assert np.max(np.abs(out[0][1] - grad)) <= 1e-8 * np.max(np.abs(grad))
+    assert out[1][0] == out[0][0] and np.array_equal(out[1][1], out[0][1])
