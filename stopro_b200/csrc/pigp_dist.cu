@@ -207,6 +207,16 @@ static bool g_side_stream = true;
 // Flag waits inside the prologue of the consuming GEMM save one tiny kernel per wait, but a grid of spinning CTAs can
 // keep this rank's own publication kernels (which a peer's progress depends on) off the SMs: off unless PIGP_FUSE_WAITS=1.
 static int g_fuse_waits = -1;
+// k-extent (in 128-tiles) of one launch of the side stream's products: PIGP_SIDE_CHUNK (default 0 = unchunked)
+static int g_side_chunk = -1;
+static int side_chunk_tiles() {
+    if (g_side_chunk < 0) {
+        const char* e = getenv("PIGP_SIDE_CHUNK");
+        g_side_chunk = e ? atoi(e) : 0;
+        if (g_side_chunk <= 0) g_side_chunk = 1 << 20;
+    }
+    return g_side_chunk;
+}
 static bool fuse_waits() {
     if (g_fuse_waits < 0) { const char* e = getenv("PIGP_FUSE_WAITS"); g_fuse_waits = (e && atoi(e) == 1) ? 1 : 0; }
     return g_fuse_waits == 1;
@@ -460,7 +470,21 @@ int rec(const Ctx& c, int c0, int nt) {
             g.kmode = 1;
             g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = c0 + n1; g.k_gt0 = c0;
             PIGP_TRY(set_wait_all(c, g, s->f_panel(k1, 0), c.sb));
-            PIGP_TRY(launch_gemm(g, c.sb));
+            // Optionally issued in k-chunks (PIGP_SIDE_CHUNK = tiles per launch): a CTA of a K = 10k product holds its SM
+            // slot for ~1 ms, and the chain's (and the publication stream's) small high-priority kernels can only start
+            // when slots drain -- stream priority does not preempt.  Measured at N = 20k: chunks of 2048 cost more GEMM
+            // efficiency than the chain gains (1 GPU 254.3 -> 256.4 ms, 2 GPUs 138.1 -> 140.0 ms), so the default is
+            // one launch.
+            const int chunk = side_chunk_tiles();
+            for (int kc = 0; kc < n1; kc += chunk) {
+                GemmDesc h = g;
+                h.A = g.A + (int64_t)kc * TILE;
+                h.B = g.B + (int64_t)kc * TILE;
+                h.K = std::min(chunk, n1 - kc) * TILE;
+                h.k_gt0 = c0 + kc;
+                if (kc > 0) h.wait_count = 0;
+                PIGP_TRY(launch_gemm(h, c.sb));
+            }
         }
     }
     return rec(c, c0 + n1, n2);
