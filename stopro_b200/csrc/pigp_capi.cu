@@ -138,14 +138,9 @@ struct pigp_solver {
     int64_t n = 0, npad = 0;
     int64_t yrow = 0;        // row of the factorisation buffer that carries y
     int64_t mrow0 = 0;       // first row available to the mixed (test x train) block
-    double* A = nullptr;     // (a_rows x npad) row-major: K -> L (-> K^-1), y row, mixed rows
+    double* A = nullptr;     // posterior only (allocated on first use): (a_rows x npad) row-major, K -> L, y row, mixed rows
     int64_t a_rows = 0;
-    double* W = nullptr;     // npad x npad, L^-1 (gradient path only)
     double* invd = nullptr;  // npad/128 inverse diagonal tiles
-    double* v = nullptr;     // npad
-    double* alpha = nullptr; // npad
-    double* trmv_part = nullptr;
-    double* partials = nullptr;
     double* out2 = nullptr;  // logdet, quad
     int32_t* info = nullptr;
     double* T = nullptr;     // test covariance scratch
@@ -360,8 +355,7 @@ int pigp_assemble_host(pigp_plan* p, const double* theta_host, double eps, int a
 void pigp_solver_destroy(pigp_solver* s) {
     if (!s) return;
     pigp_dsolver_destroy(s->ds);
-    cudaFree(s->A); cudaFree(s->W); cudaFree(s->invd); cudaFree(s->v); cudaFree(s->alpha); cudaFree(s->trmv_part);
-    cudaFree(s->partials); cudaFree(s->out2); cudaFree(s->info); cudaFree(s->T); cudaFree(s->d_theta); cudaFree(s->d_y);
+    cudaFree(s->A); cudaFree(s->invd); cudaFree(s->out2); cudaFree(s->info); cudaFree(s->T); cudaFree(s->d_theta); cudaFree(s->d_y);
     cudaFree(s->d_res); cudaFree(s->d_mu);
     if (s->h_res) cudaFreeHost(s->h_res);
     delete s;

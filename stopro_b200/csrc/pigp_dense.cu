@@ -23,10 +23,7 @@ constexpr int BM = 128;
 #ifndef PIGP_GEMM_BK
 #define PIGP_GEMM_BK 16
 #endif
-#ifndef PIGP_GEMM_STAGES
-#define PIGP_GEMM_STAGES 4
-#endif
-constexpr int BK = PIGP_GEMM_BK, STAGES = PIGP_GEMM_STAGES;
+constexpr int BK = PIGP_GEMM_BK;
 // Shared-memory operand tiles.  Fragments are fetched with 16-byte loads (two k values, or two rows, per load):
 //   k-contiguous operand  [128][BK + 8]  row stride = 8 mod 16 doubles  -> the 8 lanes of a quarter warp hit 8 distinct 16-byte slots
 //   m-contiguous operand  [BK][130]      row stride = 2 mod 8 doubles   -> same property for the (k, row-pair) pattern

@@ -318,12 +318,6 @@ int wait_all(const Ctx& c, int idx0, cudaStream_t st) {
     return PIGP_OK;
 }
 
-void set_push(const Ctx& c, GemmDesc& g, double* Cbase) {
-    g.npeers = c.npeers;
-    g.push_gm_end = c.s->T;
-    for (int k = 0; k < c.npeers; ++k) g.Cpeer[k] = c.s->peer(c.others[k], Cbase);
-}
-
 // wait for flag idx before GEMM g on stream st: fused into the GEMM prologue, or (ranks sharing a device) its own kernel
 int set_wait_one(const Ctx& c, GemmDesc& g, int idx, cudaStream_t st) {
     if (c.npeers == 0) return PIGP_OK;
