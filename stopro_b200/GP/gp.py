@@ -122,8 +122,28 @@ class GPmodel:
             self._solver = Solver(plan)
         return self._solver
 
+    def _reduce_theta(self, theta):
+        """theta as the caller holds it -> (theta the plan consumes, positions of those entries in the caller's theta or
+        None when they coincide).  params_main.yaml may carry the cross-covariance groups uxuy / uxp / uyp after the
+        ones the independent models use (default_params/sinusoidal/params_main.yaml; get_init appends them,
+        sub_modules/init_modules.py:37-48): the reference's theta slices ind_uxux / ind_uyuy / ind_pp simply never touch
+        them, so they are dropped here and their gradient is zero.  The noise parameter, if any, is the last entry."""
+        th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64).ravel())
+        n_noise = 1 if self.index_optimize_noise else 0
+        expected = self.n_kernel_theta + n_noise
+        if th.size == expected:
+            return th, None
+        if th.size < expected:
+            raise ValueError(f"theta has {th.size} entries, {type(self).__name__} needs {expected}")
+        idx = np.arange(self.n_kernel_theta)
+        if n_noise:
+            idx = np.append(idx, th.size - 1)
+        return np.ascontiguousarray(th[idx]), idx
+
     def _kernel_theta(self, theta, plan):
         th = np.asarray(theta, dtype=np.float64).ravel()
+        if th.size > self.n_kernel_theta and th.size != plan.theta_len:
+            th = th[:self.n_kernel_theta]  # unused cross-covariance groups (see _reduce_theta)
         if th.size == plan.theta_len - 1 and self.index_optimize_noise:
             th = np.append(th, 0.0)  # builders take theta without the noise entry (gp.py:221-222)
         return th
@@ -157,20 +177,25 @@ class GPmodel:
     def training_sigma(self, theta, train_pts, eps):
         """trainingK_all + add_eps_to_sigma in one kernel (gp.py:221-223)."""
         plan = self._training_plan(train_pts)
-        return plan.assemble_host(theta, eps, True)
+        return plan.assemble_host(self._reduce_theta(theta)[0], eps, True)
 
     # ------------------------------------------------------------------ likelihood and gradient
     def value_and_grad(self, theta, r, delta_y, eps, want_grad=True):
         """(NLL, dNLL/dtheta) from ONE factorisation; cached so that func(theta) followed by dfunc(theta)
         (solver/optimizers.py:148-150) costs one evaluation."""
-        th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64).ravel())
+        th, idx = self._reduce_theta(theta)
         y = np.ascontiguousarray(np.asarray(delta_y, dtype=np.float64).ravel())
         solver = self._solver_for(r)
         key = (th.tobytes(), y.tobytes(), float(eps))
         if self._cache is not None and self._cache[0] == key and (self._cache[2] is not None or not want_grad):
-            return self._cache[1], self._cache[2]
-        nll, grad, _info = solver.nll_grad_host(th, y, eps, want_grad=want_grad)
-        self._cache = (key, nll, grad)
+            nll, grad = self._cache[1], self._cache[2]
+        else:
+            nll, grad, _info = solver.nll_grad_host(th, y, eps, want_grad=want_grad)
+            self._cache = (key, nll, grad)
+        if idx is not None and grad is not None:
+            full = np.zeros(np.asarray(theta).size, dtype=np.float64)
+            full[idx] = grad
+            grad = full
         return nll, grad
 
     def trainingFunction_all(self, theta, *args):
@@ -190,7 +215,7 @@ class GPmodel:
         solver = self._solver_for(r_train)
         mixed = self._mixed_plan(r_test, r_train)
         test = self._test_plan(r_test)
-        mu, cov, _info = solver.predict_host(mixed, test, theta, delta_y_train, eps, full_cov=full_cov)
+        mu, cov, _info = solver.predict_host(mixed, test, self._reduce_theta(theta)[0], delta_y_train, eps, full_cov=full_cov)
         self._cache = None
         mus, covs, lo = [], [], 0
         for i in range(len(r_test)):
