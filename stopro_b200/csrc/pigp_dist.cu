@@ -255,6 +255,11 @@ struct pigp_dsolver {
     cudaStream_t sa = nullptr, sb = nullptr, sc = nullptr;  // sc: publication kernels (peer stores), off the chain
     cudaEvent_t ev_in = nullptr, ev_bar = nullptr, ev_b = nullptr, ev_c = nullptr, ev_out = nullptr;
     std::vector<cudaEvent_t> ev_diag, ev_upd;
+#ifdef PIGP_EXPERIMENTAL_LOOKAHEAD
+    cudaStream_t sd = nullptr;                // bulk trailing updates of the panel schedule
+    std::vector<cudaEvent_t> ev_pan, ev_next; // per coarse panel: chain done / next panel's columns updated
+    cudaEvent_t ev_d = nullptr;
+#endif
 
     int f_diag(int k) const { return k; }
     int f_panel(int k, int src) const { return T + k * world + src; }
@@ -484,6 +489,94 @@ int rec(const Ctx& c, int c0, int nt) {
     return rec(c, c0 + n1, n2);
 }
 
+#ifdef PIGP_EXPERIMENTAL_LOOKAHEAD
+// ---- EXPERIMENTAL (not compiled into the shipped library; round-2 work, never run on a GPU yet).
+// Coarse right-looking panels of W tile columns with the recursive factorisation inside a panel and a depth-1
+// look-ahead: the chain stream factors panel p (rec over its W columns, all own rows below), the bulk stream applies
+// panel p to the columns of panel p + 1 first (the chain waits only for that) and to the rest afterwards, concurrently
+// with the chain's work on panel p + 1.  The big trailing updates thereby leave the N/128-step dependency chain; the
+// L^-T products get the matching right-looking update V_p on the side stream.  Uses the existing kernels only.
+static int lookahead_width() {
+    static int w = -1;
+    if (w < 0) { const char* e = getenv("PIGP_LOOKAHEAD"); w = e ? std::max(0, atoi(e)) : 0; }
+    return w;
+}
+
+static int ensure_lookahead(pigp_dsolver* s) {
+    if (s->sd) return PIGP_OK;
+    int lo = 0, hi = 0;
+    PIGP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    PIGP_CUDA(cudaStreamCreateWithPriority(&s->sd, cudaStreamNonBlocking, lo));
+    PIGP_CUDA(cudaEventCreateWithFlags(&s->ev_d, cudaEventDisableTiming));
+    s->ev_pan.assign(s->T, nullptr);
+    s->ev_next.assign(s->T, nullptr);
+    for (int k = 0; k < s->T; ++k) {
+        PIGP_CUDA(cudaEventCreateWithFlags(&s->ev_pan[k], cudaEventDisableTiming));
+        PIGP_CUDA(cudaEventCreateWithFlags(&s->ev_next[k], cudaEventDisableTiming));
+    }
+    return PIGP_OK;
+}
+
+// C[i, J] -= L[i, Kp] L[J, Kp]^T for the own row tiles i >= jc0 (lower part), J = [jc0, jc1), Kp = [k0, k1)
+static int panel_update(const Ctx& c, int k0, int k1, int jc0, int jc1, cudaStream_t st) {
+    pigp_dsolver* s = c.s;
+    if (jc1 <= jc0) return PIGP_OK;
+    const int64_t ld = s->ld;
+    const int first = s->first_own(jc0), cnt = s->count_own(jc0, s->gy + 1);
+    if (cnt <= 0) return PIGP_OK;
+    GemmDesc g{};
+    g.M = cnt * TILE; g.N = (jc1 - jc0) * TILE; g.K = (k1 - k0) * TILE;
+    g.alpha = -1.0; g.beta = 1.0;
+    g.A = s->L + (int64_t)first * TILE * ld + (int64_t)k0 * TILE; g.lda = ld; g.a_kcontig = 1;
+    g.B = s->L + (int64_t)jc0 * TILE * ld + (int64_t)k0 * TILE; g.ldb = ld; g.b_kcontig = 1;
+    g.C = s->L + (int64_t)first * TILE * ld + (int64_t)jc0 * TILE; g.ldc = ld;
+    g.lower_only = 1;
+    g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = jc0; g.k_gt0 = k0;
+    return launch_gemm(g, st);
+}
+
+static int chol_lookahead(const Ctx& c, int W) {
+    pigp_dsolver* s = c.s;
+    PIGP_TRY(ensure_lookahead(s));
+    const int64_t ld = s->ld;
+    const int T = s->T;
+    for (int j0 = 0, p = 0; j0 < T; j0 += W, ++p) {
+        const int j1 = std::min(j0 + W, T);
+        PIGP_TRY(rec(c, j0, j1 - j0));  // chain: panel p, all own rows below (and the intra-panel L^-T products on sb)
+        if (j1 >= T) break;
+        PIGP_CUDA(cudaEventRecord(s->ev_pan[p], c.st));
+        // bulk stream: panel p -> columns of panel p + 1 (the chain waits for this), then -> everything right of it
+        PIGP_CUDA(cudaStreamWaitEvent(s->sd, s->ev_pan[p], 0));
+        PIGP_TRY(wait_all(c, s->f_panel(j1 - 1, 0), s->sd));  // every peer's rows of the panel's columns have arrived
+        const int jn = std::min(j1 + W, T);
+        PIGP_TRY(panel_update(c, j0, j1, j1, jn, s->sd));
+        PIGP_CUDA(cudaEventRecord(s->ev_next[p], s->sd));
+        PIGP_TRY(panel_update(c, j0, j1, jn, T, s->sd));
+        PIGP_CUDA(cudaStreamWaitEvent(c.st, s->ev_next[p], 0));
+        if (c.grad) {
+            // V_p: Y[j, [j1, T)] -= sum_{k in panel p, k >= j} Y[j, k] L[[j1, T), k]^T for the own row tiles j < j1
+            PIGP_CUDA(cudaStreamWaitEvent(c.sb, s->ev_pan[p], 0));
+            PIGP_TRY(wait_all(c, s->f_panel(j1 - 1, 0), c.sb));
+            const int first = s->first_own(0), cnt = s->count_own(0, j1);
+            if (cnt > 0) {
+                GemmDesc g{};
+                g.M = cnt * TILE; g.N = (T - j1) * TILE; g.K = (j1 - j0) * TILE;
+                g.alpha = -1.0; g.beta = 1.0;
+                g.A = s->Y + (int64_t)first * TILE * ld + (int64_t)j0 * TILE; g.lda = ld; g.a_kcontig = 1;
+                g.B = s->L + (int64_t)j1 * TILE * ld + (int64_t)j0 * TILE; g.ldb = ld; g.b_kcontig = 1;
+                g.C = s->Y + (int64_t)first * TILE * ld + (int64_t)j1 * TILE; g.ldc = ld;
+                g.kmode = 1;
+                g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = j1; g.k_gt0 = j0;
+                PIGP_TRY(launch_gemm(g, c.sb));
+            }
+        }
+    }
+    PIGP_CUDA(cudaEventRecord(s->ev_d, s->sd));
+    PIGP_CUDA(cudaStreamWaitEvent(c.st, s->ev_d, 0));
+    return PIGP_OK;
+}
+#endif  // PIGP_EXPERIMENTAL_LOOKAHEAD
+
 int preload_dist() {
     PIGP_TRY(preload_dense());
     PIGP_TRY(preload_assemble());
@@ -506,6 +599,12 @@ void pigp_dsolver_destroy(pigp_dsolver* s) {
     if (s->sa) cudaStreamDestroy(s->sa);
     if (s->sb) cudaStreamDestroy(s->sb);
     if (s->sc) cudaStreamDestroy(s->sc);
+#ifdef PIGP_EXPERIMENTAL_LOOKAHEAD
+    if (s->sd) cudaStreamDestroy(s->sd);
+    if (s->ev_d) cudaEventDestroy(s->ev_d);
+    for (cudaEvent_t e : s->ev_pan) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : s->ev_next) if (e) cudaEventDestroy(e);
+#endif
     for (cudaEvent_t e : {s->ev_in, s->ev_bar, s->ev_b, s->ev_c, s->ev_out}) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : s->ev_diag) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : s->ev_upd) if (e) cudaEventDestroy(e);
@@ -705,6 +804,10 @@ int pigp_dsolver_nll_grad(pigp_dsolver* s, const double* theta_dev, const double
         count_launch();
     }
     PIGP_CUDA(cudaGetLastError());
+#ifdef PIGP_EXPERIMENTAL_LOOKAHEAD
+    if (lookahead_width() > 0 && g_side_stream) PIGP_TRY(chol_lookahead(c, lookahead_width()));
+    else
+#endif
     PIGP_TRY(rec(c, 0, s->T));
     if (c.npeers > 0) {
         // the diagonal of every L_kk (log-det) travels with the DIAG flags; a GEMM only waits for the flags it consumes
