@@ -331,18 +331,15 @@ int set_wait_one(const Ctx& c, GemmDesc& g, int idx, cudaStream_t st) {
     g.wait_val = c.s->epoch; g.wait_err = c.s->err;
     return PIGP_OK;
 }
-int set_wait_all(const Ctx& c, GemmDesc& g, int idx0, cudaStream_t st) {
-    if (c.npeers == 0) return PIGP_OK;
-    return wait_all(c, idx0, st);  // never fused: the consumers are full-GPU grids (see fuse_waits)
-    g.wait_flags = c.s->flags; g.wait_idx0 = idx0; g.wait_stride = 1; g.wait_count = c.s->world; g.wait_skip = c.s->rank;
-    g.wait_val = c.s->epoch; g.wait_err = c.s->err;
-    return PIGP_OK;
+// wait for every peer's flag idx0 + src before GEMM g: always its own kernel -- the consumers are full-GPU grids, and a
+// grid of spinning CTAs keeps this rank's publication kernels off the SMs (dead-lock observed at 8 GPUs)
+int set_wait_all(const Ctx& c, GemmDesc& /*g*/, int idx0, cudaStream_t st) {
+    return wait_all(c, idx0, st);
 }
 
 // ---- merged recursion over column tiles [c0, c0 + nt): Cholesky on the chain stream; when the gradient is wanted,
-// the products of Y = L^-T that depend only on finished panels are issued on the side stream.  Flag waits are fused
-// into the prologue of the consuming GEMM and flag signals into the epilogue of the producing kernel wherever a kernel
-// exists to carry them; events order the side stream behind this rank's own producers.
+// the products of Y = L^-T that depend only on finished panels are issued on the side stream, publication to the
+// peers on the publication stream; events order those streams behind this rank's own producers, flags behind the peers'.
 PushSig make_sig(const Ctx& c, int idx) {
     PushSig sg{};
     sg.counter = c.s->sig_counter + 1; sg.idx = idx; sg.val = c.s->epoch;
