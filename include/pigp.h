@@ -12,6 +12,18 @@
  * "_host" pointers are host memory.  Functions whose name ends in _host copy
  * their inputs to the device and their results back, and synchronise the
  * stream before returning; the others never synchronise.
+ *
+ * Threads: a plan is immutable after creation (pigp_plan_set_points_host excepted) and may be shared; a solver
+ * (pigp_solver / pigp_dsolver) owns its workspace and must be used by one thread at a time -- use one solver per
+ * thread / stream.  pigp_last_error() is thread local.  The measurement aids (pigp_profile_*, pigp_set_side_stream,
+ * pigp_debug_*) are process-global switches for single-threaded benchmarks.
+ *
+ * Environment knobs read once at first use (tuning / debugging only; defaults are the measured-best settings):
+ *   PIGP_GEMM_BN=128      one 128 x 128 CTA per SM instead of two 128 x 64 CTAs
+ *   PIGP_GEMM_SMALL=0     disable the small-tile GEMM for latency-bound launches (multi-GPU needs it enabled)
+ *   PIGP_SIDE_CHUNK=<t>   issue the side stream's products in k-chunks of t tiles
+ *   PIGP_FUSE_WAITS=1     spin on the DIAG flag inside the consuming TRSM instead of a one-CTA wait kernel
+ *   PIGP_PROF_DUMP=<csv>  per-launch timeline written by pigp_profile_stop
  */
 #ifndef PIGP_H
 #define PIGP_H
