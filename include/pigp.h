@@ -20,7 +20,7 @@
  *
  * Environment knobs read once at first use (tuning / debugging only; defaults are the measured-best settings):
  *   PIGP_GEMM_BN=128      one 128 x 128 CTA per SM instead of two 128 x 64 CTAs
- *   PIGP_GEMM_SMALL=0     disable the small-tile GEMM for latency-bound launches (multi-GPU needs it enabled)
+ *   PIGP_GEMM_SMALL=0     disable the small-tile GEMM for latency-bound launches
  *   PIGP_SIDE_CHUNK=<t>   issue the side stream's products in k-chunks of t tiles
  *   PIGP_FUSE_WAITS=1     spin on the DIAG flag inside the consuming TRSM instead of a one-CTA wait kernel
  *   PIGP_PROF_DUMP=<csv>  per-launch timeline written by pigp_profile_stop
