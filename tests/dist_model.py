@@ -220,3 +220,108 @@ class Model:
                 rk.X[i] = rk.Y[rk.rows(i), i * t:] @ rk.Y[:(i + 1) * t, i * t:].T
         else:
             raise ValueError(kind)
+
+
+class AsyncModel(Model):
+    """The same numerics with the C++'s stream structure made explicit: per rank the chain stream A, the side stream B
+    (Y = L^-T products), the publication stream C and -- panel schedule only -- the bulk stream D, ordered by the events
+    the C++ records (ev_diag, ev_upd, ev_pan, ev_next, ev_b, ev_c, ev_d) and by the peer flags.  `run(seed)` executes a
+    random interleaving of all (rank, stream) queues that respects those dependencies; a dependency missing from the
+    schedule shows up as a wrong result (or NaN) for some seed."""
+
+    def _program(self, rk, schedule, panel):
+        rk.q = {"A": [], "B": [], "C": [], "D": []}
+        rk.events = set()
+        rk.head = {s: 0 for s in rk.q}
+        multi = rk.P > 1
+
+        def put(stream, op, wait=(), rec=None):
+            rk.q[stream].append(dict(op=op, wait=tuple(wait), rec=rec))
+
+        def leaf(k):
+            mine = k % rk.P == rk.r
+            if mine:
+                put("A", ("potf2", k))
+            put("A", ("nop",), rec=("ev_diag", k))
+            if mine and multi:
+                put("C", ("push_diag", k), wait=[("ev_diag", k)])
+            if not mine:
+                put("A", ("wait", ("DIAG", k)))
+            put("A", ("trsm", k), rec=("ev_upd", k))
+            if multi:
+                put("C", ("push_panel", k), wait=[("ev_upd", k)])
+            if mine:
+                put("B", ("place_diag", k), wait=[("ev_diag", k)])
+            else:
+                put("B", ("wait", ("DIAG", k)), wait=[("ev_diag", k)])
+            put("B", ("trtri_leaf", k))
+
+        def rec(c0, nt):
+            if nt == 1:
+                return leaf(c0)
+            n1 = nt // 2
+            rec(c0, n1)
+            k1 = c0 + n1 - 1
+            put("A", ("wait_panel", k1))
+            put("A", ("update", c0, c0 + n1, c0 + n1, c0 + nt))
+            put("B", ("wait_panel", k1), wait=[("ev_upd", k1)])
+            put("B", ("trtri_update", c0, c0 + n1, c0 + n1, c0 + nt))
+            rec(c0 + n1, nt - n1)
+
+        T = rk.T
+        if schedule == "recursive":
+            rec(0, T)
+        else:
+            j0, p = 0, 0
+            while j0 < T:
+                j1 = min(j0 + panel, T)
+                rec(j0, j1 - j0)
+                if j1 >= T:
+                    break
+                jn = min(j1 + panel, T)
+                put("A", ("nop",), rec=("ev_pan", p))
+                put("D", ("wait_panel", j1 - 1), wait=[("ev_pan", p)])
+                put("D", ("update", j0, j1, j1, jn), rec=("ev_next", p))
+                put("D", ("update", j0, j1, jn, T))
+                put("A", ("nop",), wait=[("ev_next", p)])
+                put("B", ("wait_panel", j1 - 1), wait=[("ev_pan", p)])
+                put("B", ("trtri_update", j0, j1, j1, T))
+                j0, p = j1, p + 1
+            put("D", ("nop",), rec=("ev_d",))
+            put("A", ("nop",), wait=[("ev_d",)])
+        if multi:  # the C++ joins the publication stream and waits for every DIAG flag only when there are peers
+            for k in range(T):
+                put("A", ("wait", ("DIAG", k)))
+            put("C", ("nop",), rec=("ev_c",))
+            put("A", ("nop",), wait=[("ev_c",)])
+        put("A", ("nll",))
+        put("B", ("nop",), rec=("ev_b",))
+        put("A", ("push_y",), wait=[("ev_b",)])
+        for src in range(rk.P):
+            if src != rk.r:
+                put("A", ("wait", ("YDONE", src)))
+        put("A", ("alpha",))
+        put("A", ("lauum",))
+
+    def run(self, seed=0):
+        rng = np.random.default_rng(seed)
+        while True:
+            ready = []
+            for rk in self.ranks:
+                for s, q in rk.q.items():
+                    h = rk.head[s]
+                    if h < len(q) and all(e in rk.events for e in q[h]["wait"]) and self._ready(rk, q[h]["op"]):
+                        ready.append((rk, s))
+            if not ready:
+                break
+            rk, s = ready[rng.integers(len(ready))]
+            item = rk.q[s][rk.head[s]]
+            if item["op"][0] != "nop":
+                self._exec(rk, item["op"])
+            if item["rec"] is not None:
+                rk.events.add(item["rec"])
+            rk.head[s] += 1
+        stuck = [(rk.r, s, q[rk.head[s]]["op"]) for rk in self.ranks for s, q in rk.q.items() if rk.head[s] < len(q)]
+        if stuck:
+            raise RuntimeError(f"dead-lock: {stuck[:4]}")
+        return self
