@@ -100,8 +100,11 @@ def test_the_async_model_detects_a_missing_dependency():
             for item in rk.q["C"]:
                 if item["op"][0] == "push_panel":
                     item["wait"] = ()
-        m.run(seed)
-        ok = all(np.allclose(Xi, Xref[rk.rows(i), :(i + 1) * tile], rtol=1e-8, atol=1e-10)
-                 for rk in m.ranks for i, Xi in rk.X.items())
+        try:
+            m.run(seed)
+            ok = all(np.allclose(Xi, Xref[rk.rows(i), :(i + 1) * tile], rtol=1e-8, atol=1e-10)
+                     for rk in m.ranks for i, Xi in rk.X.items())
+        except np.linalg.LinAlgError:  # a diagonal tile factored from unpublished (NaN / stale) panel rows
+            ok = False
         bad += not ok
     assert bad > 0
