@@ -18,14 +18,15 @@ import numpy as np
 
 
 class Rank:
-    def __init__(self, rank, world, n, tile):
+    def __init__(self, rank, world, n, tile, alloc=True):
         self.r, self.P, self.n, self.t = rank, world, n, tile
         self.T = -(-n // tile)
         self.npad = self.T * tile
         self.gy = self.first_own(self.T)
-        self.L = np.full(((self.T + world) * tile, self.npad), np.nan)
-        self.Y = np.full((self.npad, self.npad), np.nan)
-        self.invd = [np.full((tile, tile), np.nan) for _ in range(self.T)]
+        if alloc:  # tools/schedule_sim.py builds the programs only (timing model, no numerics)
+            self.L = np.full(((self.T + world) * tile, self.npad), np.nan)
+            self.Y = np.full((self.npad, self.npad), np.nan)
+            self.invd = [np.full((tile, tile), np.nan) for _ in range(self.T)]
         self.flags = {}
         self.ops, self.pc = [], 0
 
@@ -46,13 +47,15 @@ class Rank:
 
 
 class Model:
-    def __init__(self, K, y, world, tile=4, schedule="recursive", panel=2):
-        n = len(y)
+    def __init__(self, K, y, world, tile=4, schedule="recursive", panel=2, n=None):
+        """K = None builds the operation lists only (for n points), without buffers."""
+        n = len(y) if n is None else n
         self.world, self.tile, self.n = world, tile, n
-        self.ranks = [Rank(r, world, n, tile) for r in range(world)]
+        self.ranks = [Rank(r, world, n, tile, alloc=K is not None) for r in range(world)]
         self.T = self.ranks[0].T
         for rk in self.ranks:
-            self._assemble(rk, K, y)
+            if K is not None:
+                self._assemble(rk, K, y)
             self._program(rk, schedule, panel)
 
     # ---- pigp_dsolver_nll_grad prologue: own rows of K (lower), identity padding, y tile, zeroed own rows of Y
