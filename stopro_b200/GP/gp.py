@@ -41,6 +41,7 @@ class GPmodel:
         self._plans = {}
         self._solver = None
         self._cache = None  # (theta bytes, y id, eps) -> (nll, grad)
+        self._grad_seen = False  # a caller has asked for gradients: func(theta) then evaluates value AND gradient at once
 
     # ------------------------------------------------------------------ bookkeeping (gp.py:258-285)
     @staticmethod
@@ -199,11 +200,15 @@ class GPmodel:
         return nll, grad
 
     def trainingFunction_all(self, theta, *args):
+        """NLL (gp.py:213-224).  Once a gradient has been requested from this model (the explicit-derivative scripts call
+        func(theta) and then dfunc(theta) every step, solver/optimizers.py:148-150), the gradient is evaluated along with
+        the value so that the pair costs ONE factorisation instead of the reference's two."""
         r, delta_y, eps = args
-        return self.value_and_grad(theta, r, delta_y, eps, want_grad=False)[0]
+        return self.value_and_grad(theta, r, delta_y, eps, want_grad=self._grad_seen)[0]
 
     def d_trainingFunction_all(self, theta, *args):
         r, delta_y, eps = args
+        self._grad_seen = True
         return self.value_and_grad(theta, r, delta_y, eps, want_grad=True)[1].copy()
 
     def d_logposterior(self, theta, *args):
