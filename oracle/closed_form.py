@@ -88,25 +88,26 @@ def _dg_da(n, s, a):
     raise ValueError(n)
 
 
-def _prep(r, rp, dim):
-    r = np.asarray(r, dtype=np.float64)
-    rp = np.asarray(rp, dtype=np.float64)
+def _prep(r, rp, dim, dtype=np.float64):
+    r = np.asarray(r, dtype=dtype)
+    rp = np.asarray(rp, dtype=dtype)
     if dim == 1:
         r = r.reshape(-1, 1)
         rp = rp.reshape(-1, 1)
     return [r[:, None, d] - rp[None, :, d] for d in range(dim)]
 
 
-def eval_operator(name, r, rp, theta, form, dim, with_grad=False):
+def eval_operator(name, r, rp, theta, form, dim, with_grad=False, dtype=np.float64):
     """Dense block of operator ``name`` on points r (n,dim), rp (m,dim).
 
     theta = [log gamma, logl_0 .. logl_{dim-1}].  With ``with_grad`` also returns
-    d block / d theta as an array (1+dim, n, m).
+    d block / d theta as an array (1+dim, n, m).  ``dtype=np.longdouble`` evaluates the same formulas in extended
+    precision (the higher-precision truth of oracle/extended.py).
     """
-    theta = np.asarray(theta, dtype=np.float64)
+    theta = np.asarray(theta, dtype=dtype)
     gamma = np.exp(theta[0])
     a = np.exp(-2.0 * theta[1:1 + dim])
-    s = _prep(r, rp, dim)
+    s = _prep(r, rp, dim, dtype)
     E = [np.exp(-0.5 * a[d] * s[d] * s[d]) for d in range(dim)]
 
     def G(n, d):
@@ -117,7 +118,7 @@ def eval_operator(name, r, rp, theta, form, dim, with_grad=False):
         return -2.0 * a[d] * (_dg_da(n, s[d], a[d]) - 0.5 * s[d] * s[d] * _g(n, s[d], a[d])) * E[d]
 
     val = np.zeros_like(s[0])
-    grad = np.zeros((1 + dim,) + s[0].shape) if with_grad else None
+    grad = np.zeros((1 + dim,) + s[0].shape, dtype=dtype) if with_grad else None
     for coef, alpha, beta in operator_polynomial(name, dim):
         sign = coef * (-1.0) ** sum(beta)
         order = _add(alpha, beta)

@@ -26,13 +26,14 @@ from . import blocks_ref, closed_form
 
 class GPRef:
     def __init__(self, table, kernel_form="product", dim=None, lbox=None, index_optimize_noise=None,
-                 backend="closed"):
+                 backend="closed", dtype=np.float64):
         self.table = blocks_ref.TABLES[table]
         self.dim = self.table["dim"] if self.table["dim"] is not None else dim
         self.form = kernel_form if self.dim == 2 else "product"  # kernels.py:419-426: 3-D ignores kernel_form
         self.lbox = None if lbox is None else np.asarray(lbox, dtype=np.float64)
         self.index_optimize_noise = index_optimize_noise if index_optimize_noise else False
         self.backend = backend
+        self.dtype = dtype  # np.longdouble: closed-form blocks in extended precision (oracle/extended.py); closed backend only
         self._ad = None
 
     # ------------------------------------------------------------------ operators
@@ -48,14 +49,14 @@ class GPRef:
 
     def _op_eval(self, op, r, rp, theta_g):
         if self.backend == "closed":
-            return closed_form.eval_operator(op, r, rp, theta_g, self.form, self.dim)
+            return closed_form.eval_operator(op, r, rp, theta_g, self.form, self.dim, dtype=self.dtype)
         torch, ad = self._autodiff()
         t = lambda x: x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x), dtype=torch.float64)
         return ad.block(op)(t(r), t(rp), t(theta_g))
 
     def _zeros(self, n, m):
         if self.backend == "closed":
-            return np.zeros((n, m))
+            return np.zeros((n, m), dtype=self.dtype)
         return self._autodiff()[0].zeros((n, m), dtype=self._autodiff()[0].float64)
 
     def block(self, name, r, rp, theta):
@@ -131,13 +132,13 @@ class GPRef:
 
     def _theta(self, theta):
         if self.backend == "closed":
-            return np.asarray(theta, dtype=np.float64)
+            return np.asarray(theta, dtype=self.dtype)
         torch = self._autodiff()[0]
         return theta if isinstance(theta, torch.Tensor) else torch.as_tensor(np.asarray(theta), dtype=torch.float64)
 
     def _pts(self, pts):
         if self.backend == "closed":
-            return [np.asarray(p, dtype=np.float64) for p in pts]
+            return [np.asarray(p, dtype=self.dtype) for p in pts]
         torch = self._autodiff()[0]
         return [torch.as_tensor(np.asarray(p), dtype=torch.float64) for p in pts]
 
@@ -207,14 +208,14 @@ class GPRef:
 
             J = jacfwd(sigma)(self._theta(theta))  # (N, N, P)
             return [J[:, :, p].numpy() for p in range(P)]
-        return self._dK_closed(np.asarray(theta, dtype=np.float64), r)
+        return self._dK_closed(np.asarray(theta, dtype=self.dtype), r)
 
     def _dK_closed(self, theta, r):
         pts = self._pts(r)
         sec = self.calc_sec(pts)
         N = int(sec[-1])
         th, noise = self.split_hyp_and_noise(theta)
-        out = [np.zeros((N, N)) for _ in range(len(theta))]
+        out = [np.zeros((N, N), dtype=self.dtype) for _ in range(len(theta))]
         rows, blocks, groups = self.table["training"], self.table["blocks"], self.table["groups"]
         for i in range(len(pts)):
             for j in range(i, len(pts)):
@@ -224,7 +225,7 @@ class GPRef:
                     idx = list(range(len(th)))[sl]
 
                     def base(a, b):
-                        return closed_form.eval_operator(op, a, b, th[sl], self.form, self.dim, with_grad=True)[1]
+                        return closed_form.eval_operator(op, a, b, th[sl], self.form, self.dim, with_grad=True, dtype=self.dtype)[1]
 
                     a, b, l = pts[i], pts[j], self.lbox
                     if shift is None:
@@ -242,7 +243,7 @@ class GPRef:
         if self.index_optimize_noise:
             lo = int(sec[self.index_optimize_noise[0]])
             hi = int(sec[self.index_optimize_noise[-1] + 1])
-            d = np.zeros(N)
+            d = np.zeros(N, dtype=self.dtype)
             d[lo:hi] = np.exp(noise)
             out[-1] = np.diag(d)
         return out

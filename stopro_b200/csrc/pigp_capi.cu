@@ -269,8 +269,14 @@ int pigp_plan_create(const pigp_plan_desc* d, pigp_plan** out) {
             for (int t = 0; t < b.n_terms; ++t) {
                 if (b.terms[t].group < 0 || b.terms[t].group >= p->n_groups) return fail("pigp_plan_create: term group out of range");
                 if (t && b.terms[t].group < b.terms[t - 1].group) return fail("pigp_plan_create: terms must be sorted by group");
-                for (int k = 0; k < p->dim; ++k)
+                int active = 0, total = 0;
+                for (int k = 0; k < p->dim; ++k) {
                     if (b.terms[t].order[k] < -1 || b.terms[t].order[k] > 4) return fail("pigp_plan_create: derivative order out of range");
+                    if (b.terms[t].order[k] >= 0) { ++active; total += b.terms[t].order[k]; }
+                }
+                if (total > 4) return fail("pigp_plan_create: total derivative order of a term exceeds 4");
+                if (!p->product_form && p->dim > 1 && active != 1)
+                    return fail("pigp_plan_create: additive kernel form: every term must act on exactly one dimension (order -1 elsewhere)");
             }
         }
     if (cudaGetDevice(&p->device) != cudaSuccess) return fail("pigp_plan_create: no CUDA device");
@@ -300,11 +306,15 @@ int pigp_plan_create(const pigp_plan_desc* d, pigp_plan** out) {
         for (int i = 0; i < nrb; ++i)
             for (int j = 0; j < ncb; ++j) {
                 const int64_t r0 = p->sec_row[i], r1 = p->sec_row[i + 1], c0 = p->sec_col[j], c1 = p->sec_col[j + 1];
-                if (!p->symmetric || i <= j) add_tiles(full, r0, r1, c0, c1, desc_of(i, j), 0);
-                else add_tiles(full, r0, r1, c0, c1, desc_of(j, i), ASM_SWAP);  // lower block = transpose of table[j][i]
+                if (!p->symmetric) add_tiles(full, r0, r1, c0, c1, desc_of(i, j), 0);
                 if (p->symmetric && i == j) add_tiles(lower, r0, r1, c0, c1, desc_of(i, i), ASM_LOWER);
-                if (p->symmetric && i > j) add_tiles(lower, r0, r1, c0, c1, desc_of(j, i), ASM_SWAP);
+                if (p->symmetric && i > j) add_tiles(lower, r0, r1, c0, c1, desc_of(j, i), ASM_SWAP);  // lower block = transpose of table[j][i]
             }
+        if (p->symmetric) {
+            // full layout = the lower tiles, each also stored transposed: half the evaluations, exact symmetry
+            full = lower;
+            for (AsmTile& t : full) t.flags |= ASM_MIRROR;
+        }
         rc = upload_tiles(full, &p->d_tiles_full, &p->n_tiles_full);
         if (rc == PIGP_OK) rc = upload_tiles(lower, &p->d_tiles_lower, &p->n_tiles_lower);
     }

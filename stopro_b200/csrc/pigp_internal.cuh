@@ -11,7 +11,7 @@
 namespace pigp {
 
 constexpr int TILE = PIGP_TILE;        // 128: padding unit and GEMM tile
-constexpr int ASM_TR = 32;             // assembly tile rows
+constexpr int ASM_TR = 16;             // assembly tile rows
 constexpr int ASM_TC = 128;            // assembly tile cols
 constexpr int MAX_THETA = PIGP_MAX_GROUPS * 4 + 1;  // 16 kernel hyper-parameters + noise
 
@@ -69,6 +69,7 @@ enum {
     ASM_SWAP = 1,   // first kernel argument is the COLUMN point (lower half of an upper-table block)
     ASM_LOWER = 2,  // write / weigh only entries with row >= col
     ASM_PAD = 4,    // padding region: zero, 1.0 on the diagonal
+    ASM_MIRROR = 8, // also store the strictly-lower entries transposed (full layout of a symmetric matrix)
 };
 
 }  // namespace pigp

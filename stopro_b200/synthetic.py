@@ -211,3 +211,22 @@ def make_model(cfg):
                stokes3d_infer_difp=GPStokes3D, stokes3d_naive=GPStokes3DNaive, stokes2d2c=GPStokes2D2C,
                stokes2d2c_surface=GPStokes2D2CSurface)[cfg["model"]]
     return cls(Kernel=define_kernel(cfg["kernel"]), **cfg["model_kwargs"])
+
+
+def from_golden(path):
+    """A configuration whose inputs were produced by the REFERENCE's own data generator and stored in a golden fixture
+    (tests/golden/ref_c*.npz, written by tests/golden/make_golden_ref.py): the BASELINE configurations C1-C4 at their
+    true sizes (N = 32 / 498 / 1180 / 2640), including the 576 FEM test points of the sinusoidal channel."""
+    import json
+
+    g = np.load(path)
+    meta = json.loads(str(g["meta"]))
+    nb_tr, nb_te = len(g["sec_tr"]) - 1, len(g["sec_te"]) - 1
+    r_train = [g[f"r_train_{i}"] for i in range(nb_tr)]
+    f_train = [g[f"f_train_{i}"] for i in range(nb_tr)]
+    r_test = [g[f"r_test_{i}"] for i in range(nb_te)]
+    f_test = [g[f"f_test_{i}"] for i in range(nb_te)]
+    kw = {k: (np.asarray(v, dtype=np.float64) if k == "lbox" and v is not None else v)
+          for k, v in meta["model_kwargs"].items()}
+    return _pack(meta["model"], meta["model"], kw, meta["kernel"], r_train, f_train, r_test, f_test, g["theta0"],
+                 eps=float(g["eps"]))

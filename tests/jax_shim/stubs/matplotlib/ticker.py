@@ -1,0 +1,2 @@
+from _stub import install as _install
+_install(globals(), "matplotlib.ticker")
