@@ -51,21 +51,39 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=20000, help="training points (the metric is quoted at 20000)")
-    ap.add_argument("--cpu-sample-n", type=int, default=4000, help="points of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample-n", type=int, default=8000, help="points of the bounded CPU-baseline sample")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the evals/s-vs-N figures of the line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.impl == "reference" and "--cpu-sample-n" not in sys.argv:
+        # each step is one full func+dfunc evaluation of the sample: keep K steps within a few minutes of CPU time
+        a.cpu_sample_n = 8000 if a.steps <= 3 else (6400 if a.steps <= 6 else 5000)
+    return a
 
 
 # ----------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_eval(n_sample, n_full, repeats=1):
+def blas_threads(n=None):
+    """Pin the BLAS / OpenMP pools of numpy to n threads (default: every host core) and report what is in force.
+    torchrun exports OMP_NUM_THREADS=1 to its workers; the limit is therefore set at run time, not through the env."""
+    from threadpoolctl import threadpool_info, threadpool_limits
+
+    n = n or os.cpu_count() or 1
+    threadpool_limits(limits=n)
+    used = [int(p.get("num_threads", 1)) for p in threadpool_info() if p.get("user_api") in ("blas", "openmp")]
+    return max(used) if used else 1
+
+
+def cpu_reference_eval(n_sample, n_full, repeats=1, keep=False):
     """Time the restated reference (oracle.gp_ref.GPRef, reference op sequence: Cholesky, general solves against I,
-    one dense matmul per hyper-parameter -- GP/gp.py:72-89, :412-488) on an n_sample-point instance of the workload
-    and scale by the reference's (7 + 2P) N^3 cost model to n_full.  Returns (evals/s at n_full, seconds per sample)."""
+    one dense matmul per hyper-parameter -- GP/gp.py:72-89, :412-488; closed-form assembly instead of the reference's
+    autodiff, which understates the reference's cost) on an n_sample-point instance of the workload and scale by N^3 to
+    n_full ("extrapolated").  Returns (evals/s at n_full, seconds per sample, threads used, payload)."""
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from conftest import oracle_for
     from stopro_b200 import synthetic
 
+    threads = blas_threads()
     cfg = synthetic.stokes2d_scaling(n_sample, n_test=16)
     ref = oracle_for(cfg)
     args = (cfg["r_train"], cfg["delta_y"], cfg["eps"])
@@ -77,35 +95,45 @@ def cpu_reference_eval(n_sample, n_full, repeats=1):
         best = min(best, time.perf_counter() - t0)
     assert np.isfinite(f) and np.all(np.isfinite(g))
     scale = (n_full / n_sample) ** 3
-    return 1.0 / (best * scale), best
+    payload = None
+    if keep:
+        # 1-norm condition number of Sigma from its Cholesky factor (LAPACK dpocon): cheap, and what bounds the
+        # agreement two float64 evaluations can reach
+        from scipy.linalg import lapack
+        S = ref.training_sigma(cfg["theta0"], cfg["r_train"], cfg["eps"])
+        anorm = float(np.max(np.sum(np.abs(S), axis=0)))
+        c, info = lapack.dpotrf(S, lower=1, overwrite_a=1)
+        rcond, _ = lapack.dpocon(c, anorm, lower=1)
+        payload = dict(cfg=cfg, nll=float(f), grad=np.asarray(g), cond=1.0 / max(rcond, 1e-300))
+    return 1.0 / (best * scale), best, threads, payload
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count()
-    times = []
+    times, threads = [], 1
     for _ in range(args.warmup):
         cpu_reference_eval(min(args.cpu_sample_n, 1500), args.n)
     t_all0 = time.perf_counter()
     for _ in range(args.steps):
-        _, sec = cpu_reference_eval(args.cpu_sample_n, args.n)
+        _, sec, threads, _ = cpu_reference_eval(args.cpu_sample_n, args.n)
         times.append(sec)
     wall = time.perf_counter() - t_all0
     sec = sum(times) / len(times)
     scale = (args.n / args.cpu_sample_n) ** 3
     value = 1.0 / (sec * scale)
     sample = (f"one func+dfunc evaluation per step at N={args.cpu_sample_n} points of the same workload "
-              f"({sec:.2f} s each), scaled to N={args.n} by (N/Ns)^3")
+              f"({sec:.2f} s each on {threads} BLAS threads), EXTRAPOLATED to N={args.n} by (N/Ns)^3")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sec * scale, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "extrapolated": True,
         "config": {"workload": workload_name(args.n, 9, 1e-6),
-                   "parallelism": f"CPU: restated reference algorithm (oracle/, numpy + LAPACK) on {cores} host cores, rank 0 only",
+                   "parallelism": f"CPU: restated reference algorithm (oracle/, numpy + LAPACK, closed-form assembly) on "
+                                  f"{threads} BLAS threads of {os.cpu_count()} host cores, rank 0 only",
                    "sample": sample, "sample_wall_s": wall},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -152,6 +180,61 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- our arm
+def small_n_rate(n, dev):
+    """NLL+gradient evaluations/s of the C5 workload at n points on one GPU (device-resident inputs)."""
+    import torch
+    from stopro_b200 import synthetic
+
+    cfg = synthetic.stokes2d_scaling(n, n_test=16)
+    gp = synthetic.make_model(cfg)
+    gp.set_constants(cfg["r_train"], cfg["delta_y"], cfg["eps"], only_training=True)
+    solver = gp._solver_for(cfg["r_train"])
+    P = solver.plan.theta_len
+    theta = torch.as_tensor(cfg["theta0"], device=dev)
+    y = torch.as_tensor(cfg["delta_y"], device=dev)
+    out = torch.zeros(1 + P, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream or None
+
+    def step():
+        solver.nll_grad(theta.data_ptr(), y.data_ptr(), cfg["eps"], out.data_ptr(), out.data_ptr() + 8, None, stream)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    k = 20 if n < 6000 else 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(k):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ok = bool(torch.isfinite(out).all().item())
+    gp.close()
+    if not ok:
+        raise RuntimeError("non-finite result")
+    return k / (e0.elapsed_time(e1) * 1e-3)
+
+
+def bench_parity(ref, dev):
+    """GPU (through the host entry point of the C ABI) against the oracle on the instance the CPU baseline timed."""
+    import numpy as np
+    from stopro_b200 import synthetic
+
+    cfg = ref["cfg"]
+    gp = synthetic.make_model(cfg)
+    args = (cfg["r_train"], cfg["delta_y"], cfg["eps"])
+    gp.set_constants(*args, only_training=True)
+    nll, grad = gp.value_and_grad(cfg["theta0"], *args)
+    gp.close()
+    e_nll = abs(nll - ref["nll"]) / abs(ref["nll"])
+    e_grad = float(np.max(np.abs(grad - ref["grad"])) / np.max(np.abs(ref["grad"])))
+    u = 2.0 ** -53
+    tol = max(1e-8, ref["cond"] * u)
+    return {"n": int(len(cfg["delta_y"])), "eps": cfg["eps"], "nll_relerr": e_nll, "grad_relerr": e_grad,
+            "cond_1norm": ref["cond"], "tolerance": tol, "tolerance_rule": "max(1e-8, cond * 2^-53)",
+            "ok": bool(e_nll <= tol and e_grad <= tol), "against": "oracle (numpy + LAPACK restatement of the reference), same inputs"}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -213,6 +296,7 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    barrier()  # every rank has built its solver and connected its peers before the first flag wait
     for _ in range(args.warmup):
         step_device()
     sampler = ClockSampler(local)
@@ -371,12 +455,27 @@ def run_ours(args):
         "assembly": {"ms": prof["assemble"]["ms"], "gb_per_s": 8.0 * N * (N + 1) / 2 / world / (prof["assemble"]["ms"] * 1e-3) * 1e-9,
                      "hbm_peak_gb_per_s": hbm_peak()[0], "peak_source": hbm_peak()[1]},
     }
+    if world == 1 and not args.no_sweep:
+        # BASELINE.json's metric is "evals/s vs N": the sizes the reference's own scripts run (C2 498, C3 1180, C4 2640) and
+        # their scaled versions, same workload family, device-resident inputs, back-to-back evaluations
+        line["evals_per_s_vs_n"] = {}
+        for n_small in (498, 1180, 2640, 5018, 10570):
+            try:
+                line["evals_per_s_vs_n"][str(n_small)] = round(small_n_rate(n_small, dev), 2)
+            except Exception as exc:  # noqa: BLE001
+                line["evals_per_s_vs_n"][str(n_small)] = f"error: {exc}"
+        line["evals_per_s_vs_n"][str(N)] = round(line["value"], 3)
     if world == 1 and not args.no_cpu_baseline:
-        v, sec = cpu_reference_eval(args.cpu_sample_n, N)
+        v, sec, threads, ref = cpu_reference_eval(args.cpu_sample_n, N, keep=True)
         line["cpu_baseline"] = {
-            "value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-            "sample": f"one func+dfunc evaluation of the restated reference (oracle/, numpy+LAPACK) at N={args.cpu_sample_n} "
-                      f"points of the same workload: {sec:.2f} s, scaled to N={N} by (N/Ns)^3"}
+            "value": v, "unit": UNIT, "cores": threads, "kind": "port", "extrapolated": True,
+            "sample": f"one func+dfunc evaluation of the restated reference (oracle/: the reference's op sequence on numpy + "
+                      f"LAPACK, closed-form assembly in place of its autodiff) at N={args.cpu_sample_n} points of the same "
+                      f"workload: {sec:.2f} s on {threads} BLAS threads, EXTRAPOLATED to N={N} by (N/Ns)^3"}
+        # parity of the benchmark workload itself (outside every timed region): the same N = cpu_sample_n instance,
+        # eps = 1e-6, on the GPU against the oracle's values from the timing above
+        line["parity"] = bench_parity(ref, dev)
+    print(json.dumps(line), flush=True)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

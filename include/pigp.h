@@ -13,9 +13,11 @@
  * their inputs to the device and their results back, and synchronise the
  * stream before returning; the others never synchronise.
  *
- * Threads: a plan is immutable after creation (pigp_plan_set_points_host excepted) and may be shared; a solver
- * (pigp_solver / pigp_dsolver) owns its workspace and must be used by one thread at a time -- use one solver per
- * thread / stream.  pigp_last_error() is thread local.  The measurement aids (pigp_profile_*, pigp_set_side_stream,
+ * Threads: the device-pointer entry points (pigp_assemble, pigp_assemble_diag) only read a plan, so one plan may serve
+ * several threads / streams at once.  pigp_plan_set_points_host and every _host entry point use staging buffers owned by
+ * the plan or the solver and are NOT thread-safe per handle.  A solver (pigp_solver / pigp_dsolver) owns its workspace and
+ * must be used by one thread at a time -- use one solver per thread / stream.  Every entry point switches the calling
+ * thread to the device its plan was created on (cudaSetDevice).  pigp_last_error() is thread local.  The measurement aids (pigp_profile_*, pigp_set_side_stream,
  * pigp_debug_*) are process-global switches for single-threaded benchmarks.
  *
  * Environment knobs read once at first use (tuning / debugging only; defaults are the measured-best settings):
@@ -36,7 +38,7 @@ extern "C" {
 
 #define PIGP_ABI_VERSION 1
 #define PIGP_MAX_TERMS 8   /* monomials per block (3-D Kfzfz needs 7) */
-#define PIGP_MAX_GROUPS 4  /* hyper-parameter groups per model (ux, uy, uz, pp) */
+#define PIGP_MAX_GROUPS 4  /* hyper-parameter groups per model (ux, uy, uz, pp); a block may use all of them */
 #define PIGP_TILE 128      /* row/column padding unit of every factorisation buffer */
 
 enum {
@@ -48,8 +50,8 @@ enum {
 };
 
 /* One monomial of a block:  coef * gamma_g * prod_d G_{order[d]}(r_d - r'_d ; l_{g,d}),
- * G_n = (d/ds)^n exp(-s^2 / (2 l^2)).  order[d] = -1 drops dimension d from the product
- * (additive kernel form, GP/kernels.py:57-61).  Replaces the nested jax.grad / jax.hessian
+ * G_n = (d/ds)^n exp(-s^2 / (2 l^2)), sum_d order[d] <= 4.  Additive kernel form (k = gamma sum_d E_d,
+ * GP/kernels.py:57-61): exactly one order[d] >= 0 per term (the dimension the term lives on), -1 elsewhere.  Replaces the nested jax.grad / jax.hessian
  * operators of GP/gp_2D.py:16-86, GP/gp_3D.py:12-35, GP/gp_1D_laplacian.py:35-46. */
 typedef struct {
     int32_t group;     /* theta offset of the group = group * (1 + dim): [log gamma, log l_0 ..] (sub_modules/init_modules.py:5-54) */
@@ -107,7 +109,9 @@ void pigp_plan_destroy(pigp_plan* plan);
 int64_t pigp_plan_rows(const pigp_plan* plan);
 int64_t pigp_plan_cols(const pigp_plan* plan);
 int32_t pigp_plan_theta_len(const pigp_plan* plan); /* n_groups*(1+dim) (+1 when noise is optimised) */
-/* Replace the coordinates (same block sizes); side 0 = rows / first argument, 1 = columns. Async H2D on stream. */
+/* Replace the coordinates (same block sizes); side 0 = rows / first argument, 1 = columns.  The points are transposed
+ * into the plan's pinned staging buffer, copied on `stream`, and the stream is synchronised before returning (the staging
+ * buffer is reused by the next call). */
 int pigp_plan_set_points_host(pigp_plan* plan, int side, const double* pts_host, void* stream);
 
 /* trainingK_all / mixedK_all / testK_all (GP/gp.py:287-306): K_dev[row * ld + col], row-major.
@@ -116,13 +120,24 @@ int pigp_assemble(const pigp_plan* plan, const double* theta_dev, double eps, in
                   double* K_dev, int64_t ld, int layout, void* stream);
 int pigp_assemble_host(pigp_plan* plan, const double* theta_host, double eps, int add_diag,
                        double* K_host, int layout);
+/* Only the diagonal of a symmetric plan's matrix, diag_dev[rows]: what the callers of predictingFunction_all consume
+ * (std = sqrt(diag(Sigma_post)), test/test_1_sinusoidal_direct_main.py:144) -- M kernel values instead of M x M. */
+int pigp_assemble_diag(const pigp_plan* plan, const double* theta_dev, double eps, int add_diag, double* diag_dev, void* stream);
 
 /* --- solver: factorisation workspace bound to a training plan ----------------------------- */
 int pigp_solver_create(pigp_plan* training_plan, pigp_solver** out);
 void pigp_solver_destroy(pigp_solver* s);
+/* The same handle over a K dealt block-cyclically over `world` GPUs (see the multi-GPU section below): every rank creates
+ * one, wires the peers through the borrowed pigp_dsolver handle (pigp_dsolver_ipc_handle / _connect) and then all ranks
+ * issue the same sequence of pigp_nll / pigp_nll_grad / pigp_predict calls.  After a factorisation every rank holds the
+ * whole factor, so pigp_predict may be given a different (disjoint) set of test points on every rank. */
+typedef struct pigp_dsolver pigp_dsolver;
+int pigp_solver_create_dist(pigp_plan* training_plan, int rank, int world, pigp_solver** out);
+pigp_dsolver* pigp_solver_dsolver(pigp_solver* s);
 
 /* trainingFunction_all (GP/gp.py:213-224, logpGP :72-89): NLL = 0.5 |L^-1 y|^2 + sum log L_ii + 0.5 n log 2pi.
- * out_dev[0] = NLL.  info_dev (may be NULL): 0, or 1-based index of the first non-positive pivot. */
+ * out_dev[0] = NLL.  info_dev (may be NULL): 0, the 1-based index of the first non-positive pivot, or -1 when a peer's flag
+ * never arrived (multi-GPU only). */
 int pigp_nll(pigp_solver* s, const double* theta_dev, const double* y_dev, double eps,
              double* out_dev, int32_t* info_dev, void* stream);
 /* NLL and d_trainingFunction_all (GP/gp.py:412-488) from one factorisation:
@@ -145,6 +160,13 @@ int pigp_predict(pigp_solver* s, const pigp_plan* mixed, const pigp_plan* test, 
 int pigp_predict_host(pigp_solver* s, pigp_plan* mixed, pigp_plan* test, const double* theta_host,
                       const double* y_host, double eps, double* mu_host, double* cov_host, int want_full_cov,
                       int32_t* info_host);
+/* The interval_check loop of the reference's scripts (predictor(theta[i], ...) for a list of recorded hyper-parameter
+ * vectors, test/test_1_sinusoidal_direct_main.py:111-131) as ONE call: thetas_host[n_theta][theta_len] ->
+ * mu_host[n_theta][M], cov_host[n_theta][M] (or [n_theta][M][M] when want_full_cov); info_host[n_theta] (or one entry
+ * when n_theta == 1).  Results are staged on the device and copied back once. */
+int pigp_predict_batch_host(pigp_solver* s, pigp_plan* mixed, pigp_plan* test, int n_theta, const double* thetas_host,
+                            const double* y_host, double eps, double* mu_host, double* cov_host, int want_full_cov,
+                            int32_t* info_host);
 
 /* --- building blocks exposed for tests and benchmarks (device pointers, n multiple of PIGP_TILE) --- */
 /* In-place lower Cholesky of the leading n x n of A (row-major, ld), applying L^-T to the m_extra rows below it
@@ -157,7 +179,7 @@ int pigp_potrf_lower(double* A_dev, int64_t ld, int64_t n, int64_t m_extra, doub
 int pigp_potri_lower(const double* L_dev, int64_t ld, int64_t n, const double* invd_dev, double* W_dev,
                      double* X_dev, void* stream);
 /* C[MxN] = alpha * A * B^T + beta * C with A(m,k), B(n,k); *_kcontig selects which index is contiguous.
- * M, N multiples of 128, K multiple of 16.  lower_only skips tiles above the diagonal. */
+ * M, N and K multiples of 128.  lower_only skips tiles above the diagonal. */
 int pigp_dgemm(int M, int N, int K, double alpha, const double* A_dev, int64_t lda, int a_kcontig,
                const double* B_dev, int64_t ldb, int b_kcontig, double beta, double* C_dev, int64_t ldc,
                int lower_only, void* stream);
@@ -169,7 +191,6 @@ int pigp_dgemm(int M, int N, int K, double alpha, const double* A_dev, int64_t l
  * in one process).  Every rank must issue the same sequence of pigp_dsolver_nll_grad calls.  All ranks receive the
  * same NLL and (bitwise) the same gradient. */
 #define PIGP_IPC_HANDLE_BYTES 64
-typedef struct pigp_dsolver pigp_dsolver;
 int pigp_dsolver_create(pigp_plan* training_plan, int rank, int world, pigp_dsolver** out);
 void pigp_dsolver_destroy(pigp_dsolver* s);
 int pigp_dsolver_slab(const pigp_dsolver* s, void** ptr, int64_t* bytes);
@@ -188,6 +209,13 @@ int pigp_dsolver_nll_grad(pigp_dsolver* s, const double* theta_dev, const double
                           double* grad_dev, int32_t* info_dev, void* stream);
 int pigp_dsolver_nll_grad_host(pigp_dsolver* s, const double* theta_host, const double* y_host, double eps, int want_grad,
                                double* nll_host, double* grad_host, int32_t* info_host);
+/* Failure handling.  Every flag wait is bounded (PIGP_WAIT_TIMEOUT_S, default 10 s, inside a factorisation;
+ * PIGP_BARRIER_TIMEOUT_S, default 300 s, for the barrier that opens a call and absorbs host-side skew between ranks):
+ * a lost peer gives NaN results and info = -1 on every surviving rank (and PIGP_ECUDA from the _host call), never a
+ * hung GPU.  The condition is sticky; pigp_dsolver_reset -- called on EVERY rank, with a host-side barrier before the
+ * next evaluation -- drains the solver's streams and re-arms it.  Ranks must also pass a host-side barrier between
+ * pigp_dsolver_connect and their first evaluation. */
+int pigp_dsolver_reset(pigp_dsolver* s);
 
 /* Kernel launches issued by this library since load (all threads); for bench.py's gpu_launches. */
 int64_t pigp_launch_count(void);

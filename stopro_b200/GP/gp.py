@@ -10,6 +10,8 @@ A non-positive-definite K gives NaN (as jnp.linalg.cholesky does), never an exce
 A model is a list of *observables* per training / test block (see stopro_b200.operators); the block functions of
 the reference's library (Kuxux, Kfxdiv, Kuxdifux, ...) are available by name through ``model.K<a><b>(r, rp, theta)``.
 """
+import os
+
 import numpy as np
 
 from .. import _lib, operators
@@ -25,7 +27,11 @@ class GPmodel:
     #: are correlated (kept quirks, e.g. gp_sinusoidal_infer_difp.py:97)
     test_zero_blocks = frozenset()
 
-    def __init__(self, Kernel=None, index_optimize_noise=None, lbox=None):
+    def __init__(self, Kernel=None, index_optimize_noise=None, lbox=None, distributed=None, process_group=None):
+        """``distributed`` (not part of the reference's signature; default: the STOPRO_B200_DISTRIBUTED environment
+        variable): when true and a torch.distributed process group with more than one rank is up (one process per GPU,
+        e.g. under torchrun), K is dealt block-cyclically over the ranks and every rank must make the same sequence of
+        calls; all ranks receive identical results.  The YAML schema is untouched."""
         if Kernel is None:
             raise ValueError("Kernel is required (use stopro_b200.GP.kernels.define_kernel)")
         self.Kernel = Kernel
@@ -38,6 +44,9 @@ class GPmodel:
         else:
             self._obs, self._fields = operators.scalar_observables(self.dim)
         self.n_kernel_theta = len(self._fields) * (1 + self.dim)
+        if distributed is None:
+            distributed = os.environ.get("STOPRO_B200_DISTRIBUTED", "0") not in ("", "0", "false", "False")
+        self._distributed, self._group = bool(distributed), process_group
         self._plans = {}
         self._solver = None
         self._cache = None  # (theta bytes, y id, eps) -> (nll, grad)
@@ -115,13 +124,37 @@ class GPmodel:
         return self._plan("test", lambda: Plan(self.dim, self.product_form, self._fields, self._observables(te), r_test,
                                                lbox=self.lbox, zero_blocks=self.test_zero_blocks), r_test)
 
+    def _rank_world(self):
+        """(rank, world) of the sharded evaluation; (0, 1) unless ``distributed`` was asked for and a group is up."""
+        if not self._distributed:
+            return 0, 1
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()):
+            return 0, 1
+        return dist.get_rank(self._group), dist.get_world_size(self._group)
+
     def _solver_for(self, r_train):
         plan = self._training_plan(r_train)
         if self._solver is None or self._solver.plan is not plan:
             if self._solver is not None:
                 self._solver.close()
-            self._solver = Solver(plan)
+            rank, world = self._rank_world()
+            self._solver = Solver(plan, rank, world)
+            self._solver.connect_ipc(self._group)
         return self._solver
+
+    @staticmethod
+    def shard_points(pts, rank, world):
+        """The rank's share of every test block (contiguous slices): the factor is replicated after a sharded
+        factorisation, so posterior rows are independent work."""
+        out, slices = [], []
+        for p in pts:
+            n = len(p)
+            lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+            out.append(np.asarray(p)[lo:hi])
+            slices.append((lo, hi))
+        return out, slices
 
     def _reduce_theta(self, theta):
         """theta as the caller holds it -> (theta the plan consumes, positions of those entries in the caller's theta or
@@ -216,19 +249,56 @@ class GPmodel:
 
     # ------------------------------------------------------------------ posterior (gp.py:226-256)
     def predictingFunction_all(self, theta, *args, full_cov=True):
+        mus, covs = self.predict_many([theta], *args, full_cov=full_cov)
+        return mus[0], covs[0]
+
+    def predict_many(self, thetas, *args, full_cov=False):
+        """predictingFunction_all for a list of hyper-parameter vectors in one library call: the ``interval_check`` loop of
+        the reference's scripts (test/test_1_sinusoidal_direct_main.py:111-131).  Returns (list over thetas of [mu per test
+        block], list over thetas of [variance (or covariance) per test block]).  In a sharded run with diagonal-only
+        output every rank evaluates its own slice of the test points and the slices are gathered."""
         r_test, mu_test, r_train, delta_y_train, eps = args
         solver = self._solver_for(r_train)
-        mixed = self._mixed_plan(r_test, r_train)
-        test = self._test_plan(r_test)
-        mu, cov, _info = solver.predict_host(mixed, test, self._reduce_theta(theta)[0], delta_y_train, eps, full_cov=full_cov)
+        rank, world = solver.rank, solver.world
+        shard = world > 1 and not full_cov
+        pts, slices = self.shard_points(r_test, rank, world) if shard else (r_test, [(0, len(p)) for p in r_test])
+        ths = [self._reduce_theta(t)[0] for t in thetas]
+        if sum(len(p) for p in pts) > 0:
+            mixed = self._mixed_plan(pts, r_train)
+            test = self._test_plan(pts)
+            mu, cov, _info = solver.predict_batch_host(mixed, test, ths, delta_y_train, eps, full_cov=full_cov)
+        else:  # more ranks than test points: this rank only takes part in the factorisations
+            for t in ths:
+                solver.nll_grad_host(t, delta_y_train, eps, want_grad=False)
+            mu = np.zeros((len(ths), 0))
+            cov = np.zeros((len(ths), 0))
         self._cache = None
-        mus, covs, lo = [], [], 0
-        for i in range(len(r_test)):
-            hi = lo + len(r_test[i])
-            mus.append(mu[lo:hi] + np.asarray(mu_test[i], dtype=np.float64))
-            covs.append(cov[lo:hi, lo:hi].copy() if full_cov else cov[lo:hi].copy())
-            lo = hi
-        return mus, covs
+        if shard:
+            import torch.distributed as dist
+
+            parts = [None] * world
+            dist.all_gather_object(parts, (mu, cov, slices), group=self._group)
+        else:
+            parts = [(mu, cov, slices)]
+        out_mu, out_cov = [], []
+        for b in range(len(ths)):
+            mus = [np.empty(len(p)) for p in r_test]
+            covs = [np.empty((len(p), len(p)) if full_cov else len(p)) for p in r_test]
+            for pmu, pcov, psl in parts:
+                lo = 0
+                for i, (a, z) in enumerate(psl):
+                    hi = lo + (z - a)
+                    mus[i][a:z] = pmu[b, lo:hi]
+                    if full_cov:
+                        covs[i][:] = pcov[b, lo:hi, lo:hi]
+                    else:
+                        covs[i][a:z] = pcov[b, lo:hi]
+                    lo = hi
+            for i in range(len(r_test)):
+                mus[i] = mus[i] + np.asarray(mu_test[i], dtype=np.float64)
+            out_mu.append(mus)
+            out_cov.append(covs)
+        return out_mu, out_cov
 
     # ------------------------------------------------------------------ named blocks of the reference's library
     def __getattr__(self, name):

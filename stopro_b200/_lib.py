@@ -52,8 +52,11 @@ _SIGNATURES = {
     "pigp_plan_set_points_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "pigp_assemble": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "pigp_assemble_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_int]),
+    "pigp_assemble_diag": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
     "pigp_solver_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "pigp_solver_destroy": (None, [C.c_void_p]),
+    "pigp_solver_create_dist": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "pigp_solver_dsolver": (C.c_void_p, [C.c_void_p]),
     "pigp_nll": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pigp_nll_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pigp_nll_grad_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p,
@@ -62,6 +65,8 @@ _SIGNATURES = {
                                C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "pigp_predict_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
                                     C.c_void_p, C.c_int, C.c_void_p]),
+    "pigp_predict_batch_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double,
+                                          C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "pigp_potrf_lower": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pigp_potri_lower": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pigp_dgemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64,
@@ -79,6 +84,7 @@ _SIGNATURES = {
                                         C.c_void_p]),
     "pigp_dsolver_nll_grad_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_void_p]),
+    "pigp_dsolver_reset": (C.c_int, [C.c_void_p]),
     "pigp_launch_count": (C.c_int64, []),
     "pigp_set_side_stream": (C.c_int, [C.c_int]),
     "pigp_debug_potf2_stamps": (C.c_int, [C.c_void_p]),

@@ -92,23 +92,6 @@ static int upload_points(pigp_plan* p, const double* host, int64_t n, double* de
     return PIGP_OK;
 }
 
-__global__ void k_set_yrow(double* A, int64_t ld, int64_t n, int64_t npad, int64_t yrow, int block_rows, const double* y,
-                           double huge_diag) {
-    // rows [yrow, yrow + block_rows): first row = [y, 0 ..], others zero.  When the row sits inside the padded
-    // square (yrow < npad) only that single row is written and its diagonal becomes huge_diag.
-    const int64_t total = (int64_t)block_rows * npad;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = e / npad, c = e % npad;
-        double v = 0.0;
-        if (r == 0 && c < n) v = y[c];
-        if (yrow < npad) {
-            if (c > yrow) continue;  // lower storage
-            if (c == yrow) v = huge_diag;
-        }
-        A[(yrow + r) * ld + c] = v;
-    }
-}
-
 __global__ void k_rowsumsq_sub(const double* Vt, int64_t ld, int64_t m, int64_t n, const double* kdiag, double* var) {
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= m) return;
@@ -123,38 +106,53 @@ __global__ void k_rowsumsq_sub(const double* Vt, int64_t ld, int64_t m, int64_t 
     if (lane == 0) var[row] = kdiag[row] - s;
 }
 
-__global__ void k_take_diag(const double* T, int64_t ld, int64_t m, double* out) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < m) out[i] = T[i * ld + i];
-}
-
 }  // namespace pigp
 
 using namespace pigp;
 
+template <class T>
+static int grow(T** buf, int64_t* have, int64_t need) {
+    if (need <= *have) return PIGP_OK;
+    cudaFree(*buf);
+    *buf = nullptr;
+    *have = 0;
+    PIGP_CUDA(cudaMalloc(buf, sizeof(T) * (size_t)need));
+    *have = need;
+    return PIGP_OK;
+}
+
+
 struct pigp_solver {
     pigp_plan* plan = nullptr;
-    pigp_dsolver* ds = nullptr;  // world = 1 instance of the block-cyclic solver: NLL and gradient run there
+    pigp_dsolver* ds = nullptr;  // the block-cyclic solver (world = 1 unless created with _create_dist): NLL, gradient, factor
+    int world = 1;
     int64_t n = 0, npad = 0;
-    int64_t yrow = 0;        // row of the factorisation buffer that carries y
-    int64_t mrow0 = 0;       // first row available to the mixed (test x train) block
-    double* A = nullptr;     // posterior only (allocated on first use): (a_rows x npad) row-major, K -> L, y row, mixed rows
-    int64_t a_rows = 0;
-    double* invd = nullptr;  // npad/128 inverse diagonal tiles
-    double* out2 = nullptr;  // logdet, quad
     int32_t* info = nullptr;
-    double* T = nullptr;     // test covariance scratch
+    // posterior workspace (allocated on first use, grow-only)
+    double* V = nullptr;     // mpad x npad: K_ab -> K_ab L^-T
+    int64_t v_rows = 0;
+    double* T = nullptr;     // mpad x mpad test covariance (full posterior covariance only)
     int64_t t_elems = 0;
+    double* kdiag = nullptr; // diag(K_aa)
+    int64_t kdiag_elems = 0;
+    double* d_mu = nullptr;  // staging of the _host entry points: mu, then cov / var
+    double* d_cov = nullptr;
+    int64_t mu_elems = 0, cov_elems = 0;
     // staging for the _host entry points
     double* d_theta = nullptr;
     double* d_y = nullptr;
     double* d_res = nullptr;  // nll + grad
     double* h_res = nullptr;  // pinned
-    double* d_mu = nullptr;
-    int64_t mu_elems = 0;
 };
 
 static cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// every entry point works on the device its plan was created on, whatever the calling thread's current device is
+static int use_device(const pigp_plan* p) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != p->device) PIGP_CUDA(cudaSetDevice(p->device));
+    return PIGP_OK;
+}
 
 extern "C" {
 
@@ -213,6 +211,8 @@ void pigp_plan_destroy(pigp_plan* p) {
     cudaFree(p->d_table);
     cudaFree(p->d_tiles_full);
     cudaFree(p->d_tiles_lower);
+    cudaFree(p->d_tiles_diag);
+    cudaFree(p->d_khost);
     cudaFree(p->d_theta_stage);
     if (p->h_pin) cudaFreeHost(p->h_pin);
     delete p;
@@ -279,6 +279,17 @@ int pigp_plan_create(const pigp_plan_desc* d, pigp_plan** out) {
                     return fail("pigp_plan_create: additive kernel form: every term must act on exactly one dimension (order -1 elsewhere)");
             }
         }
+    if (p->product_form) {
+        // the evaluator groups the terms of a block into runs of equal (group, parity pattern of the derivative orders)
+        auto key = [&](const pigp_term& t) {
+            int pm = 0;
+            for (int k = 0; k < p->dim; ++k) pm |= (std::max(t.order[k], 0) & 1) << k;
+            return t.group * 8 + pm;
+        };
+        for (pigp_block_desc& b : p->table)
+            std::stable_sort(b.terms, b.terms + std::max(0, std::min(b.n_terms, PIGP_MAX_TERMS)),
+                             [&](const pigp_term& x, const pigp_term& y) { return key(x) < key(y); });
+    }
     if (cudaGetDevice(&p->device) != cudaSuccess) return fail("pigp_plan_create: no CUDA device");
 
     int rc = PIGP_OK;
@@ -314,8 +325,16 @@ int pigp_plan_create(const pigp_plan_desc* d, pigp_plan** out) {
             // full layout = the lower tiles, each also stored transposed: half the evaluations, exact symmetry
             full = lower;
             for (AsmTile& t : full) t.flags |= ASM_MIRROR;
+            // the diagonal alone (posterior variance: callers only ever take sqrt(diag), test_1:144): 16 x 16 tiles
+            // astride the diagonal of every diagonal block
+            std::vector<AsmTile> diag;
+            for (int i = 0; i < nrb; ++i)
+                for (int64_t r = p->sec_row[i]; r < p->sec_row[i + 1]; r += ASM_TR)
+                    diag.push_back(AsmTile{(int32_t)r, (int32_t)r, (int32_t)std::min<int64_t>(ASM_TR, p->sec_row[i + 1] - r),
+                                           (int32_t)std::min<int64_t>(ASM_TR, p->sec_row[i + 1] - r), desc_of(i, i), ASM_DIAG});
+            rc = upload_tiles(diag, &p->d_tiles_diag, &p->n_tiles_diag);
         }
-        rc = upload_tiles(full, &p->d_tiles_full, &p->n_tiles_full);
+        if (rc == PIGP_OK) rc = upload_tiles(full, &p->d_tiles_full, &p->n_tiles_full);
         if (rc == PIGP_OK) rc = upload_tiles(lower, &p->d_tiles_lower, &p->n_tiles_lower);
     }
     if (rc != PIGP_OK) { pigp_plan_destroy(p); return rc; }
@@ -329,6 +348,7 @@ int32_t pigp_plan_theta_len(const pigp_plan* p) { return p ? p->theta_len : 0; }
 
 int pigp_plan_set_points_host(pigp_plan* p, int side, const double* pts_host, void* stream) {
     if (!p || !pts_host) { set_error("pigp_plan_set_points_host: null argument"); return PIGP_EINVAL; }
+    PIGP_TRY(use_device(p));
     if (side == 0 || p->symmetric) return upload_points(p, pts_host, p->rows, p->d_pts_row, as_stream(stream));
     return upload_points(p, pts_host, p->cols, p->d_pts_col, as_stream(stream));
 }
@@ -336,6 +356,7 @@ int pigp_plan_set_points_host(pigp_plan* p, int side, const double* pts_host, vo
 int pigp_assemble(const pigp_plan* p, const double* theta_dev, double eps, int add_diag, double* K_dev, int64_t ld,
                   int layout, void* stream) {
     if (!p || !theta_dev || !K_dev || ld < p->cols) { set_error("pigp_assemble: bad argument"); return PIGP_EINVAL; }
+    PIGP_TRY(use_device(p));
     if (add_diag && !p->symmetric) { set_error("pigp_assemble: add_diag needs a symmetric plan"); return PIGP_EINVAL; }
     if (layout == PIGP_LAYOUT_LOWER) {
         if (!p->symmetric) { set_error("pigp_assemble: LOWER layout needs a symmetric plan"); return PIGP_EINVAL; }
@@ -346,57 +367,55 @@ int pigp_assemble(const pigp_plan* p, const double* theta_dev, double eps, int a
 
 int pigp_assemble_host(pigp_plan* p, const double* theta_host, double eps, int add_diag, double* K_host, int layout) {
     if (!p || !theta_host || !K_host) { set_error("pigp_assemble_host: null argument"); return PIGP_EINVAL; }
-    double* K = nullptr;
+    PIGP_TRY(use_device(p));
     const size_t bytes = sizeof(double) * (size_t)p->rows * p->cols;
-    PIGP_CUDA(cudaMalloc(&K, bytes));
-    int rc = PIGP_OK;
-    if (cudaMemcpy(p->d_theta_stage, theta_host, sizeof(double) * p->theta_len, cudaMemcpyHostToDevice) != cudaSuccess) rc = PIGP_ECUDA;
-    if (rc == PIGP_OK && layout == PIGP_LAYOUT_LOWER && cudaMemset(K, 0, bytes) != cudaSuccess) rc = PIGP_ECUDA;
-    if (rc == PIGP_OK) rc = pigp_assemble(p, p->d_theta_stage, eps, add_diag, K, p->cols, layout, nullptr);
-    if (rc == PIGP_OK && cudaMemcpy(K_host, K, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) {
-        set_error("pigp_assemble_host: device to host copy failed");
-        rc = PIGP_ECUDA;
+    if (bytes > p->d_khost_bytes) {  // grow-only staging buffer owned by the plan (not thread-safe per plan: see pigp.h)
+        cudaFree(p->d_khost);
+        p->d_khost = nullptr;
+        p->d_khost_bytes = 0;
+        PIGP_CUDA(cudaMalloc(&p->d_khost, bytes));
+        p->d_khost_bytes = bytes;
     }
-    cudaFree(K);
-    return rc;
+    double* K = p->d_khost;
+    PIGP_CUDA(cudaMemcpy(p->d_theta_stage, theta_host, sizeof(double) * p->theta_len, cudaMemcpyHostToDevice));
+    if (layout == PIGP_LAYOUT_LOWER) PIGP_CUDA(cudaMemset(K, 0, bytes));
+    PIGP_TRY(pigp_assemble(p, p->d_theta_stage, eps, add_diag, K, p->cols, layout, nullptr));
+    PIGP_CUDA(cudaMemcpy(K_host, K, bytes, cudaMemcpyDeviceToHost));
+    return PIGP_OK;
+}
+
+int pigp_assemble_diag(const pigp_plan* p, const double* theta_dev, double eps, int add_diag, double* diag_dev, void* stream) {
+    if (!p || !theta_dev || !diag_dev || !p->symmetric) { set_error("pigp_assemble_diag: needs a symmetric plan and device buffers"); return PIGP_EINVAL; }
+    return launch_assemble(p, p->d_tiles_diag, p->n_tiles_diag, theta_dev, eps, add_diag, diag_dev, 0, as_stream(stream));
 }
 
 // ------------------------------------------------------------------------------------------------ solver
 void pigp_solver_destroy(pigp_solver* s) {
     if (!s) return;
     pigp_dsolver_destroy(s->ds);
-    cudaFree(s->A); cudaFree(s->invd); cudaFree(s->out2); cudaFree(s->info); cudaFree(s->T); cudaFree(s->d_theta); cudaFree(s->d_y);
-    cudaFree(s->d_res); cudaFree(s->d_mu);
+    cudaFree(s->info); cudaFree(s->V); cudaFree(s->T); cudaFree(s->kdiag); cudaFree(s->d_mu); cudaFree(s->d_cov);
+    cudaFree(s->d_theta); cudaFree(s->d_y); cudaFree(s->d_res);
     if (s->h_res) cudaFreeHost(s->h_res);
     delete s;
 }
 
-static int ensure_rows(pigp_solver* s, int64_t rows) {
-    if (rows <= s->a_rows) return PIGP_OK;
-    if (s->A) cudaFree(s->A);
-    s->A = nullptr;
-    s->a_rows = 0;
-    PIGP_CUDA(cudaMalloc(&s->A, sizeof(double) * (size_t)rows * s->npad));
-    s->a_rows = rows;
-    return PIGP_OK;
-}
+int pigp_solver_create(pigp_plan* plan, pigp_solver** out) { return pigp_solver_create_dist(plan, 0, 1, out); }
 
-int pigp_solver_create(pigp_plan* plan, pigp_solver** out) {
+pigp_dsolver* pigp_solver_dsolver(pigp_solver* s) { return s ? s->ds : nullptr; }
+
+int pigp_solver_create_dist(pigp_plan* plan, int rank, int world, pigp_solver** out) {
     if (!plan || !out || !plan->symmetric) { set_error("pigp_solver_create: needs a symmetric training plan"); return PIGP_EINVAL; }
     *out = nullptr;
+    PIGP_TRY(use_device(plan));
     pigp_solver* s = new pigp_solver();
     s->plan = plan;
+    s->world = world;
     s->n = plan->rows;
     s->npad = round_up(s->n, TILE);
-    if (s->n < s->npad) { s->yrow = s->n; s->mrow0 = s->npad; }          // y rides in the first padding row
-    else { s->yrow = s->npad; s->mrow0 = s->npad + TILE; }                // no padding row: y gets its own block
-    int rc = pigp_dsolver_create(plan, 0, 1, &s->ds);  // A (posterior only) is allocated on first use
+    int rc = pigp_dsolver_create(plan, rank, world, &s->ds);
     auto cuda_ok = [&](cudaError_t e, const char* what) {
         if (e != cudaSuccess && rc == PIGP_OK) { set_error(std::string(what) + ": " + cudaGetErrorString(e)); rc = PIGP_ECUDA; }
     };
-    const int64_t nt = s->npad / TILE;
-    cuda_ok(cudaMalloc(&s->invd, sizeof(double) * nt * TILE * TILE), "cudaMalloc invd");
-    cuda_ok(cudaMalloc(&s->out2, sizeof(double) * 2), "cudaMalloc out2");
     cuda_ok(cudaMalloc(&s->info, sizeof(int32_t)), "cudaMalloc info");
     cuda_ok(cudaMalloc(&s->d_theta, sizeof(double) * MAX_THETA), "cudaMalloc theta");
     cuda_ok(cudaMalloc(&s->d_y, sizeof(double) * s->n), "cudaMalloc y");
@@ -407,34 +426,42 @@ int pigp_solver_create(pigp_plan* plan, pigp_solver** out) {
     return PIGP_OK;
 }
 
-// assemble K (lower, jitter added), pad, place y, factor with `extra_rows` more rows under the square
-static int factor(pigp_solver* s, const double* theta, const double* y, double eps, int64_t extra_rows, int32_t* info,
-                  cudaStream_t st) {
-    const pigp_plan* p = s->plan;
-    const int64_t ld = s->npad;
-    PIGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
-    PIGP_TRY(launch_assemble(p, p->d_tiles_lower, p->n_tiles_lower, theta, eps, 1, s->A, ld, st));
-    PIGP_TRY(launch_pad(s->A, ld, s->n, s->n, s->npad, s->npad, 1, 1, st));
-    const int yblock = (s->yrow < s->npad) ? 1 : TILE;
-    {
-        ProfScope prof(PROF_MISC, st);
-        k_set_yrow<<<(unsigned)std::min<int64_t>((yblock * s->npad + 255) / 256, 1184), 256, 0, st>>>(
-            s->A, ld, s->n, s->npad, s->yrow, yblock, y, 1e300);
-        count_launch();
+// V[:, tiles c0 .. c0 + nt) <- V L^-T restricted to those columns: recursive (the flops are GEMMs with large K), the
+// leaf multiplies by the inverse diagonal tile in place
+static int trsm_rec(double* V, int64_t ldv, int64_t m, const FactorView& f, int c0, int nt, cudaStream_t st) {
+    if (nt == 1) {
+        GemmDesc g{};
+        g.M = (int)m; g.N = TILE; g.K = TILE;
+        g.alpha = 1.0; g.beta = 0.0;
+        g.A = V + (int64_t)c0 * TILE; g.lda = ldv; g.a_kcontig = 1;
+        g.B = f.invd + (int64_t)c0 * TILE * TILE; g.ldb = TILE; g.b_kcontig = 1;
+        g.C = V + (int64_t)c0 * TILE; g.ldc = ldv;
+        g.force_bn128 = 1;  // in place: a CTA reads its 128 columns of its rows before it writes them
+        return launch_gemm(g, st);
     }
-    PIGP_CUDA(cudaGetLastError());
-    return potrf_lower(s->A, ld, s->npad, (s->mrow0 - s->npad) + extra_rows, s->invd, info, st);
+    const int n1 = nt / 2, n2 = nt - n1;
+    PIGP_TRY(trsm_rec(V, ldv, m, f, c0, n1, st));
+    GemmDesc g{};
+    g.M = (int)m; g.N = n2 * TILE; g.K = n1 * TILE;
+    g.alpha = -1.0; g.beta = 1.0;
+    g.A = V + (int64_t)c0 * TILE; g.lda = ldv; g.a_kcontig = 1;
+    g.B = f.L + (int64_t)(c0 + n1) * TILE * f.ld + (int64_t)c0 * TILE; g.ldb = f.ld; g.b_kcontig = 1;
+    g.C = V + (int64_t)(c0 + n1) * TILE; g.ldc = ldv;
+    PIGP_TRY(launch_gemm(g, st));
+    return trsm_rec(V, ldv, m, f, c0 + n1, n2, st);
 }
 
 int pigp_nll(pigp_solver* s, const double* theta_dev, const double* y_dev, double eps, double* out_dev, int32_t* info_dev,
              void* stream) {
     if (!s || !theta_dev || !y_dev || !out_dev) { set_error("pigp_nll: null argument"); return PIGP_EINVAL; }
+    PIGP_TRY(use_device(s->plan));
     return pigp_dsolver_nll_grad(s->ds, theta_dev, y_dev, eps, out_dev, nullptr, info_dev ? info_dev : s->info, stream);
 }
 
 int pigp_nll_grad(pigp_solver* s, const double* theta_dev, const double* y_dev, double eps, double* nll_dev, double* grad_dev,
                   int32_t* info_dev, void* stream) {
     if (!s || !theta_dev || !y_dev || !nll_dev || !grad_dev) { set_error("pigp_nll_grad: null argument"); return PIGP_EINVAL; }
+    PIGP_TRY(use_device(s->plan));
     return pigp_dsolver_nll_grad(s->ds, theta_dev, y_dev, eps, nll_dev, grad_dev, info_dev ? info_dev : s->info, stream);
 }
 
@@ -442,9 +469,12 @@ int pigp_nll_grad_host(pigp_solver* s, const double* theta_host, const double* p
                        int want_grad, double* nll_host, double* grad_host, int32_t* info_host) {
     if (!s || !theta_host || !y_host || !nll_host || (want_grad && !grad_host)) { set_error("pigp_nll_grad_host: null argument"); return PIGP_EINVAL; }
     pigp_plan* p = s->plan;
+    PIGP_TRY(use_device(p));
     const int P = p->theta_len;
     cudaStream_t st = 0;
     if (pts_host) PIGP_TRY(upload_points(p, pts_host, p->rows, p->d_pts_row, st));
+    if (s->world > 1)  // sharded: the block-cyclic solver's own host entry point (own stream, time-out reporting)
+        return pigp_dsolver_nll_grad_host(s->ds, theta_host, y_host, eps, want_grad, nll_host, grad_host, info_host);
     double* h_theta = s->h_res + 2 + MAX_THETA;
     double* h_y = h_theta + MAX_THETA;
     std::memcpy(h_theta, theta_host, sizeof(double) * P);
@@ -470,46 +500,40 @@ int pigp_predict(pigp_solver* s, const pigp_plan* mixed, const pigp_plan* test, 
         set_error("pigp_predict: mixed must be (test x train) and test symmetric over the same test points");
         return PIGP_EINVAL;
     }
+    PIGP_TRY(use_device(s->plan));
     cudaStream_t st = as_stream(stream);
     int32_t* info = info_dev ? info_dev : s->info;
     const int64_t m = mixed->rows, mpad = round_up(m, TILE), ld = s->npad;
-    PIGP_TRY(ensure_rows(s, s->mrow0 + mpad));
-    double* Vt = s->A + s->mrow0 * ld;
-    // mixed block under the square: rows = test points (first kernel argument), columns = training points
-    PIGP_TRY(launch_assemble(mixed, mixed->d_tiles_full, mixed->n_tiles_full, theta_dev, 0.0, 0, Vt, ld, st));
-    PIGP_TRY(launch_pad(Vt, ld, m, s->n, mpad, s->npad, 0, 0, st));
-    PIGP_TRY(factor(s, theta_dev, y_dev, eps, mpad, info, st));
+    PIGP_TRY(grow(&s->V, &s->v_rows, mpad));
+    // L and L^-1 y from the solver's own factorisation (the NLL value is a by-product, parked in d_res)
+    PIGP_TRY(pigp_dsolver_nll_grad(s->ds, theta_dev, y_dev, eps, s->d_res, nullptr, info, stream));
+    const FactorView f = factor_view(s->ds);
+    // V = K_ab L^-T: rows = test points (first kernel argument), columns = training points
+    PIGP_TRY(launch_assemble(mixed, mixed->d_tiles_full, mixed->n_tiles_full, theta_dev, 0.0, 0, s->V, ld, st));
+    PIGP_TRY(launch_pad(s->V, ld, m, s->n, mpad, s->npad, 0, 0, st));
+    PIGP_TRY(trsm_rec(s->V, ld, mpad, f, 0, f.T, st));
     // mu = K_ab K_bb^-1 y = (K_ab L^-T)(L^-1 y)
-    PIGP_TRY(launch_gemv(Vt, ld, m, s->n, s->A + s->yrow * ld, mu_dev, st));
-    // K_aa - V^T V
-    if (s->t_elems < mpad * mpad) {
-        if (s->T) cudaFree(s->T);
-        s->T = nullptr; s->t_elems = 0;
-        PIGP_CUDA(cudaMalloc(&s->T, sizeof(double) * (size_t)mpad * mpad));
-        s->t_elems = mpad * mpad;
-    }
-    PIGP_TRY(launch_assemble(test, test->d_tiles_full, test->n_tiles_full, theta_dev, 0.0, 0, s->T, mpad, st));
-    PIGP_TRY(launch_pad(s->T, mpad, m, m, mpad, mpad, 0, 0, st));
+    PIGP_TRY(launch_gemv(s->V, ld, m, s->n, f.v, mu_dev, st));
     if (want_full_cov) {
+        // K_aa - V V^T
+        PIGP_TRY(grow(&s->T, &s->t_elems, mpad * mpad));
+        PIGP_TRY(launch_assemble(test, test->d_tiles_full, test->n_tiles_full, theta_dev, 0.0, 0, s->T, mpad, st));
+        PIGP_TRY(launch_pad(s->T, mpad, m, m, mpad, mpad, 0, 0, st));
         GemmDesc g{};
         g.M = (int)mpad; g.N = (int)mpad; g.K = (int)s->npad;
         g.alpha = -1.0; g.beta = 1.0;
-        g.A = Vt; g.lda = ld; g.a_kcontig = 1;
-        g.B = Vt; g.ldb = ld; g.b_kcontig = 1;
+        g.A = s->V; g.lda = ld; g.a_kcontig = 1;
+        g.B = s->V; g.ldb = ld; g.b_kcontig = 1;
         g.C = s->T; g.ldc = mpad;
         PIGP_TRY(launch_gemm(g, st));
         PIGP_CUDA(cudaMemcpy2DAsync(cov_dev, sizeof(double) * m, s->T, sizeof(double) * mpad, sizeof(double) * m, m,
                                     cudaMemcpyDeviceToDevice, st));
     } else {
-        if (s->mu_elems < m) {
-            if (s->d_mu) cudaFree(s->d_mu);
-            s->d_mu = nullptr; s->mu_elems = 0;
-            PIGP_CUDA(cudaMalloc(&s->d_mu, sizeof(double) * m));
-            s->mu_elems = m;
-        }
-        k_take_diag<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(s->T, mpad, m, s->d_mu);
-        k_rowsumsq_sub<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(Vt, ld, m, s->n, s->d_mu, cov_dev);
-        count_launch(2);
+        // only diag(K_aa) is evaluated (M values, not M x M) and only the row norms of V are formed
+        PIGP_TRY(grow(&s->kdiag, &s->kdiag_elems, mpad));
+        PIGP_TRY(launch_assemble(test, test->d_tiles_diag, test->n_tiles_diag, theta_dev, 0.0, 0, s->kdiag, 0, st));
+        k_rowsumsq_sub<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(s->V, ld, m, s->n, s->kdiag, cov_dev);
+        count_launch();
         PIGP_CUDA(cudaGetLastError());
     }
     return PIGP_OK;
@@ -517,28 +541,35 @@ int pigp_predict(pigp_solver* s, const pigp_plan* mixed, const pigp_plan* test, 
 
 int pigp_predict_host(pigp_solver* s, pigp_plan* mixed, pigp_plan* test, const double* theta_host, const double* y_host,
                       double eps, double* mu_host, double* cov_host, int want_full_cov, int32_t* info_host) {
-    if (!s || !mixed || !test || !theta_host || !y_host || !mu_host || !cov_host) { set_error("pigp_predict_host: null argument"); return PIGP_EINVAL; }
+    return pigp_predict_batch_host(s, mixed, test, 1, theta_host, y_host, eps, mu_host, cov_host, want_full_cov, info_host);
+}
+
+int pigp_predict_batch_host(pigp_solver* s, pigp_plan* mixed, pigp_plan* test, int n_theta, const double* thetas_host,
+                            const double* y_host, double eps, double* mu_host, double* cov_host, int want_full_cov,
+                            int32_t* info_host) {
+    if (!s || !mixed || !test || !thetas_host || !y_host || !mu_host || !cov_host || n_theta < 1) { set_error("pigp_predict_batch_host: bad argument"); return PIGP_EINVAL; }
+    PIGP_TRY(use_device(s->plan));
     const int P = s->plan->theta_len;
     const int64_t m = mixed->rows;
-    const size_t cov_elems = want_full_cov ? (size_t)m * m : (size_t)m;
-    double *d_mu = nullptr, *d_cov = nullptr;
-    PIGP_CUDA(cudaMalloc(&d_mu, sizeof(double) * m));
-    if (cudaMalloc(&d_cov, sizeof(double) * cov_elems) != cudaSuccess) { cudaFree(d_mu); set_error("pigp_predict_host: out of memory"); return PIGP_ENOMEM; }
-    int rc = PIGP_OK;
-    auto ck = [&](cudaError_t e) { if (e != cudaSuccess && rc == PIGP_OK) { set_error(cudaGetErrorString(e)); rc = PIGP_ECUDA; } };
-    ck(cudaMemcpy(s->d_theta, theta_host, sizeof(double) * P, cudaMemcpyHostToDevice));
-    ck(cudaMemcpy(s->d_y, y_host, sizeof(double) * s->n, cudaMemcpyHostToDevice));
-    if (rc == PIGP_OK) rc = pigp_predict(s, mixed, test, s->d_theta, s->d_y, eps, d_mu, d_cov, want_full_cov, s->info, nullptr);
-    if (rc == PIGP_OK) {
-        ck(cudaMemcpy(mu_host, d_mu, sizeof(double) * m, cudaMemcpyDeviceToHost));
-        ck(cudaMemcpy(cov_host, d_cov, sizeof(double) * cov_elems, cudaMemcpyDeviceToHost));
+    const int64_t cov_each = want_full_cov ? m * m : m;
+    // results of all n_theta evaluations are staged on the device and copied back once
+    PIGP_TRY(grow(&s->d_mu, &s->mu_elems, m * n_theta));
+    PIGP_TRY(grow(&s->d_cov, &s->cov_elems, cov_each * n_theta));
+    PIGP_CUDA(cudaMemcpy(s->d_y, y_host, sizeof(double) * s->n, cudaMemcpyHostToDevice));
+    int32_t worst = 0;
+    for (int b = 0; b < n_theta; ++b) {
+        PIGP_CUDA(cudaMemcpy(s->d_theta, thetas_host + (int64_t)b * P, sizeof(double) * P, cudaMemcpyHostToDevice));
+        PIGP_TRY(pigp_predict(s, mixed, test, s->d_theta, s->d_y, eps, s->d_mu + (int64_t)b * m, s->d_cov + (int64_t)b * cov_each,
+                              want_full_cov, s->info, nullptr));
         int32_t inf = 0;
-        ck(cudaMemcpy(&inf, s->info, sizeof(int32_t), cudaMemcpyDeviceToHost));
-        if (info_host) *info_host = inf;
+        PIGP_CUDA(cudaMemcpy(&inf, s->info, sizeof(int32_t), cudaMemcpyDeviceToHost));  // also orders theta's reuse
+        if (inf != 0 && worst == 0) worst = inf;
+        if (info_host && n_theta > 1) info_host[b] = inf;
     }
-    cudaFree(d_mu);
-    cudaFree(d_cov);
-    return rc;
+    PIGP_CUDA(cudaMemcpy(mu_host, s->d_mu, sizeof(double) * m * n_theta, cudaMemcpyDeviceToHost));
+    PIGP_CUDA(cudaMemcpy(cov_host, s->d_cov, sizeof(double) * cov_each * n_theta, cudaMemcpyDeviceToHost));
+    if (info_host && n_theta == 1) *info_host = worst;
+    return PIGP_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ building blocks

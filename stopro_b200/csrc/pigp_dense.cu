@@ -99,7 +99,7 @@ __device__ __forceinline__ void wait_flags(const GemmDesc& g, int tid) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
             if (v >= g.wait_val) break;
             asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(now));
-            if (now - t0 > 4000000000ull) { atomicExch(g.wait_err, 1); break; }
+            if (now - t0 > g.wait_timeout_ns) { atomicExch(g.wait_err, 1); break; }
             __nanosleep(64);
         }
     }

@@ -36,9 +36,9 @@ __global__ void k_signal(PeerFlags pf, int idx, u64 val) {
     }
 }
 
-// thread t waits until flags[idx0 + t * stride] >= val (t == skip is not waited for).  Bounded: after ~4 s the error
-// flag is raised and the kernel returns, so a lost peer can never hang the device.
-__global__ void k_wait(const u64* flags, int idx0, int stride, int count, int skip, u64 val, int* err) {
+// thread t waits until flags[idx0 + t * stride] >= val (t == skip is not waited for).  Bounded: after timeout_ns the
+// error flag is raised and the kernel returns, so a lost peer can never hang the device.
+__global__ void k_wait(const u64* flags, int idx0, int stride, int count, int skip, u64 val, int* err, u64 timeout_ns) {
     const int t = threadIdx.x;
     if (t >= count || t == skip) return;
     const u64* p = flags + idx0 + (int64_t)t * stride;
@@ -50,7 +50,7 @@ __global__ void k_wait(const u64* flags, int idx0, int stride, int count, int sk
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
         if (v >= val) break;
         asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(now));
-        if (now - t0 > 4000000000ull) { atomicExch(err, 1); break; }
+        if (now - t0 > timeout_ns) { atomicExch(err, 1); break; }
         __nanosleep(100);
     }
 }
@@ -174,9 +174,10 @@ __global__ void k_sum_slots(const double* slots, int world, int len, double* out
     out[i] = s;
 }
 
-__global__ void k_finish_nll_d(const double* out2, int64_t n, const int32_t* info, const int* err, double* nll) {
+__global__ void k_finish_nll_d(const double* out2, int64_t n, int32_t* info, const int* err, double* nll) {
     double v = 0.5 * out2[1] + out2[0] + 0.5 * (double)n * log(2.0 * 3.14159265358979323846);  // GP/gp.py:85-89
-    if ((info && *info != 0) || (err && *err != 0)) v = nan("");
+    if (err && *err != 0) *info = -1;  // a peer's flag never arrived: reported through info (device-pointer API) as well
+    if (*info != 0) v = nan("");
     *nll = v;
 }
 
@@ -217,6 +218,19 @@ static int side_chunk_tiles() {
     }
     return g_side_chunk;
 }
+// Time-outs of the flag waits.  Inside a factorisation every rank is running, so a flag that stays down for seconds
+// means a lost peer (PIGP_WAIT_TIMEOUT_S, default 10 s).  The barrier that opens a call also absorbs host-side skew
+// between the ranks -- first-call module loading, a slow set_points on one rank, a garbage-collection pause -- and gets
+// its own, much longer limit (PIGP_BARRIER_TIMEOUT_S, default 300 s).
+static u64 env_seconds_ns(const char* name, double dflt) {
+    const char* e = getenv(name);
+    double v = e ? atof(e) : dflt;
+    if (!(v > 0.0)) v = dflt;
+    return (u64)(v * 1e9);
+}
+static u64 wait_timeout_ns() { static u64 v = env_seconds_ns("PIGP_WAIT_TIMEOUT_S", 10.0); return v; }
+static u64 barrier_timeout_ns() { static u64 v = env_seconds_ns("PIGP_BARRIER_TIMEOUT_S", 300.0); return v; }
+
 static bool fuse_waits() {
     if (g_fuse_waits < 0) { const char* e = getenv("PIGP_FUSE_WAITS"); g_fuse_waits = (e && atoi(e) == 1) ? 1 : 0; }
     return g_fuse_waits == 1;
@@ -241,6 +255,7 @@ struct pigp_dsolver {
     bool shared_device = false;  // a peer rank lives on this device (tests): flag waits stay in their own 1-CTA kernels,
                                  // because a grid of spinning CTAs could starve the producer it is waiting for
     u64 epoch = 0;
+    bool broken = false;  // an enqueue failed part-way through a call: the solver must be reset (or destroyed)
     // private (not shared)
     AsmTile* d_tiles = nullptr;
     int64_t n_tiles = 0;
@@ -271,6 +286,15 @@ struct pigp_dsolver {
     int first_own(int a) const { return a + ((rank - a) % world + world) % world; }
     int count_own(int a, int b) const { const int f = first_own(a); return f < b ? (b - f + world - 1) / world : 0; }
 };
+
+namespace pigp {
+FactorView factor_view(pigp_dsolver* s) {
+    FactorView f{};
+    f.L = s->L; f.ld = s->ld; f.npad = s->npad; f.T = s->T; f.invd = s->invd;
+    f.v = s->L + (int64_t)s->gy * TILE * s->ld;  // first row of the y tile: L^-1 y after the factorisation
+    return f;
+}
+}  // namespace pigp
 
 namespace {
 
@@ -307,17 +331,18 @@ int signal(const Ctx& c, int idx) {
 int wait_one(const Ctx& c, int idx, cudaStream_t st) {
     if (c.npeers == 0) return PIGP_OK;
     ProfScope prof(PROF_MISC, st);
-    k_wait<<<1, 32, 0, st>>>(c.s->flags, idx, 0, 1, -1, c.s->epoch, c.s->err);
+    k_wait<<<1, 32, 0, st>>>(c.s->flags, idx, 0, 1, -1, c.s->epoch, c.s->err, wait_timeout_ns());
     count_launch();
     PIGP_CUDA(cudaGetLastError());
     return PIGP_OK;
 }
 
 // flags[idx0 + src] for every src != rank
-int wait_all(const Ctx& c, int idx0, cudaStream_t st) {
+int wait_all(const Ctx& c, int idx0, cudaStream_t st, u64 timeout_ns = 0) {
     if (c.npeers == 0) return PIGP_OK;
     ProfScope prof(PROF_MISC, st);
-    k_wait<<<1, 32, 0, st>>>(c.s->flags, idx0, 1, c.s->world, c.s->rank, c.s->epoch, c.s->err);
+    k_wait<<<1, 32, 0, st>>>(c.s->flags, idx0, 1, c.s->world, c.s->rank, c.s->epoch, c.s->err,
+                             timeout_ns ? timeout_ns : wait_timeout_ns());
     count_launch();
     PIGP_CUDA(cudaGetLastError());
     return PIGP_OK;
@@ -328,7 +353,7 @@ int set_wait_one(const Ctx& c, GemmDesc& g, int idx, cudaStream_t st) {
     if (c.npeers == 0) return PIGP_OK;
     if (c.s->shared_device || !fuse_waits()) return wait_one(c, idx, st);
     g.wait_flags = c.s->flags; g.wait_idx0 = idx; g.wait_stride = 0; g.wait_count = 1; g.wait_skip = -1;
-    g.wait_val = c.s->epoch; g.wait_err = c.s->err;
+    g.wait_val = c.s->epoch; g.wait_err = c.s->err; g.wait_timeout_ns = wait_timeout_ns();
     return PIGP_OK;
 }
 // wait for every peer's flag idx0 + src before GEMM g: always its own kernel -- the consumers are full-GPU grids, and a
@@ -762,26 +787,48 @@ int pigp_device_uuid(void* out16) {
     return PIGP_OK;
 }
 
+static int dsolver_enqueue(pigp_dsolver* s, const double* theta_dev, const double* y_dev, double eps, double* nll_dev,
+                           double* grad_dev, int32_t* info_dev, cudaStream_t st);
+
 int pigp_dsolver_nll_grad(pigp_dsolver* s, const double* theta_dev, const double* y_dev, double eps, double* nll_dev,
                           double* grad_dev, int32_t* info_dev, void* stream) {
     if (!s || !theta_dev || !y_dev || !nll_dev) { set_error("pigp_dsolver_nll_grad: null argument"); return PIGP_EINVAL; }
     if (!s->connected) { set_error("pigp_dsolver_nll_grad: peers are not connected"); return PIGP_EINVAL; }
+    if (s->broken) { set_error("pigp_dsolver_nll_grad: an earlier call failed part-way; call pigp_dsolver_reset on every rank"); return PIGP_ECUDA; }
     cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
     cudaStream_t st = s->sa;
+    {
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != s->plan->device) PIGP_CUDA(cudaSetDevice(s->plan->device));
+    }
+    PIGP_CUDA(cudaEventRecord(s->ev_in, user));
+    PIGP_CUDA(cudaStreamWaitEvent(st, s->ev_in, 0));
+    s->epoch += 1;
+    // From here on the peers expect this rank's publications of epoch `epoch`: if an enqueue fails below, the call still
+    // joins the user's stream to whatever was enqueued (so nothing runs unordered) and the solver is marked broken; the
+    // peers' waits for the missing flags end at their time-out with info = -1 / NaN results.
+    const int rc = dsolver_enqueue(s, theta_dev, y_dev, eps, nll_dev, grad_dev, info_dev, st);
+    if (rc != PIGP_OK) s->broken = true;
+    const cudaError_t e1 = cudaEventRecord(s->ev_out, st);
+    const cudaError_t e2 = (e1 == cudaSuccess) ? cudaStreamWaitEvent(user, s->ev_out, 0) : e1;
+    if (rc != PIGP_OK) return rc;
+    if (e2 != cudaSuccess) { s->broken = true; set_error(std::string("pigp_dsolver_nll_grad: ") + cudaGetErrorString(e2)); return PIGP_ECUDA; }
+    return PIGP_OK;
+}
+
+static int dsolver_enqueue(pigp_dsolver* s, const double* theta_dev, const double* y_dev, double eps, double* nll_dev,
+                           double* grad_dev, int32_t* info_dev, cudaStream_t st) {
     const pigp_plan* p = s->plan;
     const int64_t ld = s->ld;
-    s->epoch += 1;
     Ctx c = make_ctx(s, st);
     c.sb = g_side_stream ? s->sb : st;  // serial mode (per-kernel timing): everything on the chain stream
     c.sc = g_side_stream ? s->sc : st;
     c.grad = grad_dev != nullptr;
     int32_t* info = s->info;
-    PIGP_CUDA(cudaEventRecord(s->ev_in, user));
-    PIGP_CUDA(cudaStreamWaitEvent(st, s->ev_in, 0));
     PIGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
     // every peer has finished reading what the previous call left in this rank's buffers
     PIGP_TRY(signal(c, s->f_bar(s->rank)));
-    PIGP_TRY(wait_all(c, s->f_bar(0), st));
+    PIGP_TRY(wait_all(c, s->f_bar(0), st, barrier_timeout_ns()));
     const int first = s->first_own(0), cnt = s->count_own(0, s->T);
     if (c.grad) {
         PIGP_CUDA(cudaEventRecord(s->ev_bar, st));
@@ -810,7 +857,7 @@ int pigp_dsolver_nll_grad(pigp_dsolver* s, const double* theta_dev, const double
         // the diagonal of every L_kk (log-det) travels with the DIAG flags; a GEMM only waits for the flags it consumes
         ProfScope prof(PROF_MISC, st);
         for (int k0 = 0; k0 < s->T; k0 += 32) {
-            k_wait<<<1, 32, 0, st>>>(s->flags, s->f_diag(k0), 1, std::min(32, s->T - k0), -1, s->epoch, s->err);
+            k_wait<<<1, 32, 0, st>>>(s->flags, s->f_diag(k0), 1, std::min(32, s->T - k0), -1, s->epoch, s->err, wait_timeout_ns());
             count_launch();
         }
         PIGP_CUDA(cudaGetLastError());
@@ -878,8 +925,20 @@ int pigp_dsolver_nll_grad(pigp_dsolver* s, const double* theta_dev, const double
         PIGP_CUDA(cudaGetLastError());
     }
     if (info_dev) PIGP_CUDA(cudaMemcpyAsync(info_dev, info, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-    PIGP_CUDA(cudaEventRecord(s->ev_out, st));
-    PIGP_CUDA(cudaStreamWaitEvent(user, s->ev_out, 0));
+    return PIGP_OK;
+}
+
+int pigp_dsolver_reset(pigp_dsolver* s) {
+    if (!s) { set_error("pigp_dsolver_reset: null solver"); return PIGP_EINVAL; }
+    // Drain this rank's streams and clear the sticky time-out flag.  Call it on EVERY rank after a failed evaluation
+    // (info = -1, NaN results or PIGP_ECUDA from a _host call), with a host-side barrier between the resets and the
+    // next evaluation; epochs keep counting, so stale flags of the failed call are never mistaken for new ones.
+    PIGP_CUDA(cudaStreamSynchronize(s->sa));
+    PIGP_CUDA(cudaStreamSynchronize(s->sb));
+    PIGP_CUDA(cudaStreamSynchronize(s->sc));
+    PIGP_CUDA(cudaMemset(s->err, 0, sizeof(int)));
+    PIGP_CUDA(cudaMemset(s->sig_counter, 0, 2 * sizeof(unsigned int)));
+    s->broken = false;
     return PIGP_OK;
 }
 

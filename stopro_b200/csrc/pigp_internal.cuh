@@ -11,7 +11,7 @@
 namespace pigp {
 
 constexpr int TILE = PIGP_TILE;        // 128: padding unit and GEMM tile
-constexpr int ASM_TR = 16;             // assembly tile rows
+constexpr int ASM_TR = 64;             // assembly tile rows (a multiple of 16; 128 must be a multiple of it)
 constexpr int ASM_TC = 128;            // assembly tile cols
 constexpr int MAX_THETA = PIGP_MAX_GROUPS * 4 + 1;  // 16 kernel hyper-parameters + noise
 
@@ -70,6 +70,7 @@ enum {
     ASM_LOWER = 2,  // write / weigh only entries with row >= col
     ASM_PAD = 4,    // padding region: zero, 1.0 on the diagonal
     ASM_MIRROR = 8, // also store the strictly-lower entries transposed (full layout of a symmetric matrix)
+    ASM_DIAG = 16,  // store only the diagonal entries (R == C), to K[R]: the diagonal of a symmetric matrix as a vector
 };
 
 }  // namespace pigp
@@ -93,6 +94,10 @@ struct pigp_plan {
     int64_t n_tiles_full = 0;
     pigp::AsmTile* d_tiles_lower = nullptr;  // symmetric plans only
     int64_t n_tiles_lower = 0;
+    pigp::AsmTile* d_tiles_diag = nullptr;   // symmetric plans only: the diagonal as a vector
+    int64_t n_tiles_diag = 0;
+    double* d_khost = nullptr;               // staging of pigp_assemble_host (grow-only)
+    size_t d_khost_bytes = 0;
     double* d_theta_stage = nullptr;  // MAX_THETA doubles, for the _host entry points
     double* h_pin = nullptr;          // pinned staging
     int64_t h_pin_bytes = 0;
@@ -112,6 +117,16 @@ int launch_grad(const pigp_plan* p, const AsmTile* tiles, int64_t n_tiles, const
 // lower-triangle tiles of a symmetric plan whose 128-row tile belongs to `rank` (tile t -> rank t mod world); tiles never
 // straddle a 128-row boundary
 void build_lower_tiles_owned(const pigp_plan* p, int rank, int world, std::vector<AsmTile>& out);
+
+// ---- what the posterior driver needs of a (world = 1) block-cyclic solver after an NLL evaluation (pigp_dist.cu)
+struct FactorView {
+    double* L;       // lower Cholesky factor, row-major, leading dimension ld (npad rows)
+    int64_t ld, npad;
+    int T;           // npad / 128
+    double* invd;    // T inverse diagonal tiles
+    double* v;       // L^-1 y (npad entries; zeros beyond n)
+};
+FactorView factor_view(pigp_dsolver* s);
 
 // ---- dense linear algebra (pigp_dense.cu)
 struct GemmDesc {
@@ -138,6 +153,7 @@ struct GemmDesc {
     const unsigned long long* wait_flags;
     int wait_idx0, wait_stride, wait_count, wait_skip;
     unsigned long long wait_val;
+    unsigned long long wait_timeout_ns;
     int* wait_err;
     // ---- flag signal fused into the epilogue: the last of sig_total CTAs stores sig_val to the sig_n peer flags
     // (small-tile kernel only; sig_total must equal the number of CTAs that reach the epilogue)

@@ -118,6 +118,10 @@ class Plan:
                                                  int(layout)))
         return K
 
+    def assemble_diag(self, theta_ptr, eps, add_diag, out_ptr, stream=None):
+        """Only the diagonal of a symmetric plan's matrix (device pointers)."""
+        _lib.check(_lib.lib().pigp_assemble_diag(self.handle, theta_ptr, float(eps), int(add_diag), out_ptr, stream))
+
     def assemble(self, theta_ptr, eps, add_diag, out_ptr, ld, layout=_lib.LAYOUT_FULL, stream=None):
         """Device-pointer form (theta_ptr / out_ptr are integers, e.g. torch.Tensor.data_ptr())."""
         _lib.check(_lib.lib().pigp_assemble(self.handle, theta_ptr, float(eps), int(add_diag), out_ptr, int(ld), int(layout),
@@ -125,18 +129,67 @@ class Plan:
 
 
 class Solver:
-    def __init__(self, plan):
+    """Factorisation workspace bound to a training plan (pigp_solver).  With world > 1 the covariance matrix is dealt
+    block-cyclically over the ranks of one NVLink box (one process per GPU): every rank creates Solver(plan, rank, world),
+    calls connect_ipc() once, and then all ranks issue the same sequence of evaluations."""
+
+    def __init__(self, plan, rank=0, world=1):
         if not plan.symmetric:
             raise ValueError("Solver needs the symmetric training plan")
-        self.plan = plan
+        self.plan, self.rank, self.world = plan, int(rank), int(world)
         h = C.c_void_p()
-        _lib.check(_lib.lib().pigp_solver_create(plan.handle, C.byref(h)))
+        _lib.check(_lib.lib().pigp_solver_create_dist(plan.handle, self.rank, self.world, C.byref(h)))
         self.handle = h
+        self._opened = []
+
+    # -- multi-GPU wiring (no-ops for world == 1)
+    @property
+    def _ds(self):
+        return C.c_void_p(_lib.lib().pigp_solver_dsolver(self.handle))
+
+    def connect_ipc(self, group=None):
+        """Exchange the CUDA-IPC handles of the solver slabs over torch.distributed (any backend) and map the peers."""
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+
+        from .dist import exchange_handles
+
+        lib = _lib.lib()
+        buf = (C.c_char * _lib.IPC_HANDLE_BYTES)()
+        _lib.check(lib.pigp_dsolver_ipc_handle(self._ds, buf))
+        uuid = (C.c_char * 16)()
+        _lib.check(lib.pigp_device_uuid(uuid))
+        both = exchange_handles(bytes(buf) + bytes(uuid), group)
+        slab, nbytes = C.c_void_p(), C.c_int64()
+        _lib.check(lib.pigp_dsolver_slab(self._ds, C.byref(slab), C.byref(nbytes)))
+        slabs, shared = [], False
+        for r, b in enumerate(both):
+            if r == self.rank:
+                slabs.append(slab.value)
+                continue
+            shared |= b[_lib.IPC_HANDLE_BYTES:] == bytes(uuid)
+            ptr = C.c_void_p()
+            _lib.check(lib.pigp_ipc_open(b[:_lib.IPC_HANDLE_BYTES], C.byref(ptr)))
+            self._opened.append(ptr.value)
+            slabs.append(ptr.value)
+        arr = (C.c_void_p * self.world)(*[C.c_void_p(p) for p in slabs])
+        _lib.check(lib.pigp_dsolver_connect(self._ds, arr))
+        _lib.check(lib.pigp_dsolver_set_shared_device(self._ds, int(shared)))
+        dist.barrier(group=group)  # every rank is wired before anyone's first flag wait
+
+    def reset(self):
+        """Re-arm after a failed sharded evaluation (call on every rank, then barrier)."""
+        if self.world > 1:
+            _lib.check(_lib.lib().pigp_dsolver_reset(self._ds))
 
     def close(self):
         if getattr(self, "handle", None):
             _lib.lib().pigp_solver_destroy(self.handle)
             self.handle = None
+            for ptr in self._opened:
+                _lib.lib().pigp_ipc_close(ptr)
+            self._opened = []
 
     def __del__(self):
         try:
@@ -171,14 +224,20 @@ class Solver:
         _lib.check(_lib.lib().pigp_nll(self.handle, theta_ptr, y_ptr, float(eps), nll_ptr, info_ptr, stream))
 
     def predict_host(self, mixed, test, theta, y, eps, full_cov=True):
+        mu, cov, info = self.predict_batch_host(mixed, test, [theta], y, eps, full_cov=full_cov)
+        return mu[0], cov[0], int(info[0])
+
+    def predict_batch_host(self, mixed, test, thetas, y, eps, full_cov=False):
+        """Posterior for a list of hyper-parameter vectors in ONE library call (the interval_check loop of the reference's
+        scripts) -> mu (n_theta, M), cov (n_theta, M[, M]), info (n_theta,)."""
         p = self.plan
-        th = p._theta(theta)
+        th = np.ascontiguousarray(np.stack([p._theta(t) for t in thetas]))
         yy = np.ascontiguousarray(np.asarray(y, dtype=np.float64).ravel())
-        m = mixed.rows
-        mu = np.empty(m, dtype=np.float64)
-        cov = np.empty((m, m) if full_cov else (m,), dtype=np.float64)
-        info = C.c_int32()
-        _lib.check(_lib.lib().pigp_predict_host(self.handle, mixed.handle, test.handle, th.ctypes.data, yy.ctypes.data,
-                                                float(eps), mu.ctypes.data, cov.ctypes.data, int(full_cov),
-                                                C.addressof(info)))
-        return mu, cov, info.value
+        nb, m = len(th), mixed.rows
+        mu = np.empty((nb, m), dtype=np.float64)
+        cov = np.empty((nb, m, m) if full_cov else (nb, m), dtype=np.float64)
+        info = np.zeros(nb, dtype=np.int32)
+        _lib.check(_lib.lib().pigp_predict_batch_host(self.handle, mixed.handle, test.handle, nb, th.ctypes.data,
+                                                      yy.ctypes.data, float(eps), mu.ctypes.data, cov.ctypes.data,
+                                                      int(full_cov), info.ctypes.data))
+        return mu, cov, info

@@ -45,17 +45,22 @@ class FakePlan:
 class FakeSolver:
     created = []
 
-    def __init__(self, plan):
-        self.plan, self.evals, self.closed = plan, 0, False
+    def __init__(self, plan, rank=0, world=1):
+        self.plan, self.evals, self.closed, self.rank, self.world = plan, 0, False, rank, world
         FakeSolver.created.append(self)
+
+    def connect_ipc(self, group=None):
+        pass
 
     def nll_grad_host(self, th, y, eps, want_grad=True, pts=None):
         self.evals += 1
         return float(np.sum(th) + np.sum(y)), (np.arange(len(th), dtype=float) if want_grad else None), 0
 
-    def predict_host(self, mixed, test, theta, y, eps, full_cov=True):
-        m = mixed.rows
-        return np.arange(m, dtype=float), (np.eye(m) if full_cov else np.ones(m)), 0
+    def predict_batch_host(self, mixed, test, thetas, y, eps, full_cov=True):
+        m, nb = mixed.rows, len(thetas)
+        mu = np.tile(np.arange(m, dtype=float), (nb, 1)) + np.arange(nb)[:, None]
+        cov = np.tile(np.eye(m), (nb, 1, 1)) if full_cov else np.ones((nb, m))
+        return mu, cov, np.zeros(nb, dtype=np.int32)
 
     def close(self):
         self.closed = True
@@ -145,3 +150,28 @@ def test_kernel_is_required_and_close_releases_everything(model):
     assert all(p.closed for p in FakePlan.created) and all(s.closed for s in FakeSolver.created)
     with pytest.raises(ValueError):
         type(gp)(Kernel=None)
+
+
+def test_predict_many_is_one_call_per_list_and_splits_per_block(model):
+    cfg, gp = model
+    args = (cfg["r_test"], cfg["mu_test"], cfg["r_train"], cfg["delta_y"], cfg["eps"])
+    gp.set_constants(*args)
+    thetas = [cfg["theta0"], cfg["theta0"] + 0.1, cfg["theta0"] - 0.2]
+    mus, vars_ = gp.predict_many(thetas, *args)
+    assert len(mus) == 3 and len(vars_) == 3
+    sizes = [len(r) for r in cfg["r_test"]]
+    for b in range(3):
+        assert [len(m) for m in mus[b]] == sizes and [len(v) for v in vars_[b]] == sizes
+        flat = np.concatenate(mus[b])
+        assert np.allclose(flat, np.arange(sum(sizes)) + b)           # per-theta result, blocks in order, mu_test = 0 added
+
+
+def test_shard_points_partitions_every_block():
+    pts = [np.arange(10.0).reshape(5, 2), np.arange(14.0).reshape(7, 2), np.zeros((0, 2))]
+    seen = [np.zeros(len(p), dtype=int) for p in pts]
+    for rank in range(3):
+        part, slices = gp_module.GPmodel.shard_points(pts, rank, 3)
+        for i, ((lo, hi), q) in enumerate(zip(slices, part)):
+            assert len(q) == hi - lo and np.array_equal(q, pts[i][lo:hi])
+            seen[i][lo:hi] += 1
+    assert all(np.all(s == 1) for s in seen)

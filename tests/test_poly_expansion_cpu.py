@@ -1,5 +1,5 @@
 """Host-side model of the assembly kernel's arithmetic (csrc/pigp_assemble.cu): the descriptor -> dense polynomial
-expansion of its prologue (herm_coef, poly_expo, the -2k rule for d/dlog l) and the nested-Horner order of poly_eval,
+expansion of its prologue (herm_coef, the parity classes, the -2k rule for d/dlog l) and the evaluation order of rpoly_eval / upoly_eval,
 restated in numpy and checked against the closed-form oracle for every block of the Stokes libraries.  It pins the
 algebra the CUDA code relies on without needing a GPU."""
 import itertools
@@ -13,19 +13,22 @@ from stopro_b200 import operators
 MAX_DEG = 4
 
 
-def expo_order(dim):
-    out = []
-    for i0 in range(MAX_DEG, -1, -1):
-        if dim == 1:
-            out.append((i0,))
-            continue
-        for i1 in range(MAX_DEG - i0, -1, -1):
-            if dim == 2:
-                out.append((i0, i1))
-                continue
-            for i2 in range(MAX_DEG - i0 - i1, -1, -1):
-                out.append((i0, i1, i2))
-    return out
+KEXP = {1: [(2,), (1,), (0,)],
+        2: [(2, 0), (1, 1), (1, 0), (0, 2), (0, 1), (0, 0)],
+        3: [(2, 0, 0), (1, 1, 0), (1, 0, 1), (1, 0, 0), (0, 2, 0), (0, 1, 1), (0, 1, 0), (0, 0, 2), (0, 0, 1), (0, 0, 0)]}
+
+
+def rpoly(c, x, dim):
+    """rpoly_eval of the kernel: R(x_0 .. x_{D-1}), total degree <= 2, coefficients in KEXP order."""
+    if dim == 1:
+        return (c[0] * x[0] + c[1]) * x[0] + c[2]
+    if dim == 2:
+        t0 = c[0] * x[0] + (c[1] * x[1] + c[2])
+        t1 = c[3] * x[1] + c[4]
+        return t0 * x[0] + (t1 * x[1] + c[5])
+    t0 = c[0] * x[0] + (c[1] * x[1] + (c[2] * x[2] + c[3]))
+    t1 = c[4] * x[1] + (c[5] * x[2] + c[6])
+    return t0 * x[0] + (t1 * x[1] + ((c[7] * x[2] + c[8]) * x[2] + c[9]))
 
 
 def herm_coef(n, i, a):
@@ -36,28 +39,11 @@ def herm_coef(n, i, a):
     return table[n][i]
 
 
-def horner(c, s, dim):
-    """poly_eval of the kernel: coefficients consumed in expo_order."""
-    idx = 0
-    acc = None
-    for i0 in range(MAX_DEG, -1, -1):
-        if dim == 1:
-            acc = c[idx] if acc is None else acc * s[0] + c[idx]
-            idx += 1
-            continue
-        q = None
-        for i1 in range(MAX_DEG - i0, -1, -1):
-            if dim == 2:
-                q = c[idx] if q is None else q * s[1] + c[idx]
-                idx += 1
-                continue
-            w = None
-            for i2 in range(MAX_DEG - i0 - i1, -1, -1):
-                w = c[idx] if w is None else w * s[2] + c[idx]
-                idx += 1
-            q = w if q is None else q * s[1] + w
-        acc = q if acc is None else acc * s[0] + q
-    assert idx == len(c)
+def horner1(c, s):
+    """upoly_eval of the kernel (additive form): c4 .. c0."""
+    acc = c[0]
+    for ci in c[1:]:
+        acc = acc * s + ci
     return acc
 
 
@@ -72,24 +58,30 @@ def kernel_model(terms, theta, s, dim, product):
         gamma = np.exp(theta[g * (1 + dim)])
         a = np.exp(-2.0 * theta[g * (1 + dim) + 1:(g + 1) * (1 + dim)])
         if product:
-            expo = expo_order(dim)
-            coef = np.zeros((1 + dim, len(expo)))
-            for m, e in enumerate(expo):
-                for _, c, order in run:
-                    p, ks = c, []
-                    for d in range(dim):
-                        n = max(order[d], 0)
-                        p *= herm_coef(n, e[d], a[d])
-                        ks.append((n + e[d]) >> 1)
-                    coef[0, m] += p
-                    for d in range(dim):
-                        coef[1 + d, m] += -2.0 * ks[d] * p
+            # runs of equal (group, parity pattern), as pigp_plan_create sorts them
+            classes = sorted({tuple(max(o, 0) & 1 for o in t[2]) for t in run})
             E = gamma * np.exp(-0.5 * np.sum(a * s * s))
-            P = horner(coef[0], s, dim)
-            val += P * E
-            grad[g * (1 + dim)] += P * E
-            for d in range(dim):
-                grad[g * (1 + dim) + 1 + d] += E * (a[d] * s[d] * s[d] * P + horner(coef[1 + d], s, dim))
+            x = s * s
+            for pm in classes:
+                sub = [t for t in run if tuple(max(o, 0) & 1 for o in t[2]) == pm]
+                coef = np.zeros((1 + dim, len(KEXP[dim])))
+                for m, kx in enumerate(KEXP[dim]):
+                    for _, c, order in sub:
+                        p, ks = c, []
+                        for d in range(dim):
+                            n = max(order[d], 0)
+                            i = pm[d] + 2 * kx[d]
+                            p *= herm_coef(n, i, a[d])
+                            ks.append((n + i) >> 1)
+                        coef[0, m] += p
+                        for d in range(dim):
+                            coef[1 + d, m] += -2.0 * ks[d] * p
+                pref = np.prod([s[d] if pm[d] else 1.0 for d in range(dim)])
+                P = rpoly(coef[0], x, dim)
+                val += pref * P * E
+                grad[g * (1 + dim)] += pref * P * E
+                for d in range(dim):
+                    grad[g * (1 + dim) + 1 + d] += pref * E * (a[d] * x[d] * P + rpoly(coef[1 + d], x, dim))
         else:
             for d in range(dim):
                 c0, c1 = np.zeros(5), np.zeros(5)
@@ -103,10 +95,10 @@ def kernel_model(terms, theta, s, dim, product):
                         c1[m] += -2.0 * ((order[d] + i) >> 1) * p
                 t = a[d] * s[d] * s[d]
                 E = gamma * np.exp(-0.5 * t)
-                P = horner(c0, s[d:d + 1], 1)
+                P = horner1(c0, s[d])
                 val += P * E
                 grad[g * (1 + dim)] += P * E
-                grad[g * (1 + dim) + 1 + d] += E * (t * P + horner(c1, s[d:d + 1], 1))
+                grad[g * (1 + dim) + 1 + d] += E * (t * P + horner1(c1, s[d]))
     return val, grad
 
 
