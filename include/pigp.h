@@ -168,6 +168,20 @@ int pigp_predict_batch_host(pigp_solver* s, pigp_plan* mixed, pigp_plan* test, i
                             const double* y_host, double eps, double* mu_host, double* cov_host, int want_full_cov,
                             int32_t* info_host);
 
+/* optimize_by_adam (solver/optimizers.py:94-263) with the hyper-parameters, the Adam moments and the histories resident
+ * on the device: per iteration one NLL + gradient evaluation and one update kernel, enqueued back to back; the host reads
+ * the state every check_every iterations.  Semantics kept: loss = (NLL + sum(theta) [+ ridge_alpha sum exp(theta)^2]) /
+ * ntraining, gradient = (dNLL + 1 [+ ridge term when ridge_in_grad: the autodiff scripts; the explicit-derivative scripts
+ * drop it, GP/gp.py:491-493]) / ntraining, optax.adam defaults, entries with fixed_host[i] != 0 held fixed
+ * (index_fixed), stop when |loss_t - loss_{t-1}| < stop_eps twice in a row.
+ * Outputs: theta_hist_host[(n_done + 1) x P] (row 0 = theta0), loss_hist_host[n_done + 1] (entry 0 = "loss before
+ * optimize" = entry 1), norm_hist_host[n_done]; *status_host: 0 max_iter reached, 1 converged, 2 gradient NaN,
+ * 3 theta NaN, 4 initial loss NaN (the reference raises in cases 2-4). */
+int pigp_adam_host(pigp_solver* s, const double* theta0_host, const double* y_host, double eps, int max_iter, double lr,
+                   double stop_eps, double ntraining, double ridge_alpha, int ridge_in_grad, const int32_t* fixed_host,
+                   int check_every, double* theta_hist_host, double* loss_hist_host, double* norm_hist_host,
+                   int32_t* n_done_host, int32_t* status_host);
+
 /* --- building blocks exposed for tests and benchmarks (device pointers, n multiple of PIGP_TILE) --- */
 /* In-place lower Cholesky of the leading n x n of A (row-major, ld), applying L^-T to the m_extra rows below it
  * (jnp.linalg.cholesky + jnp.linalg.solve of GP/gp.py:83-84, :106-118).  invd_dev: n/128 inverse diagonal tiles

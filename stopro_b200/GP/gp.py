@@ -244,6 +244,19 @@ class GPmodel:
         self._grad_seen = True
         return self.value_and_grad(theta, r, delta_y, eps, want_grad=True)[1].copy()
 
+    def adam_device(self, theta0, r, delta_y, eps, max_iter, lr, stop_eps, ntraining, ridge_alpha=0.0, ridge_in_grad=True,
+                    fixed=None, check_every=16):
+        """optimize_by_adam's loop (solver/optimizers.py:173-235) resident on the device.  Returns (theta history
+        (n+1, P_caller), loss history, gradient-norm history, status) or None when theta carries extra entries that are
+        held by the caller only (cross-covariance groups of the YAML schema)."""
+        th, idx = self._reduce_theta(theta0)
+        if idx is not None:
+            return None
+        solver = self._solver_for(r)
+        self._cache = None
+        return solver.adam_host(th, delta_y, eps, max_iter, lr, stop_eps, ntraining, ridge_alpha=ridge_alpha,
+                                ridge_in_grad=ridge_in_grad, fixed=fixed, check_every=check_every)
+
     def d_logposterior(self, theta, *args):
         return self.d_trainingFunction_all(theta, *args) + 1.0  # gradient of the sum(theta) prior (gp.py:491-493)
 

@@ -106,6 +106,86 @@ __global__ void k_rowsumsq_sub(const double* Vt, int64_t ld, int64_t m, int64_t 
     if (lane == 0) var[row] = kdiag[row] - s;
 }
 
+// ---- device-resident optimiser step (solver/optimizers.py:173-235): one warp, thread i owns hyper-parameter i
+struct AdamArgs {
+    int P, max_iter;
+    double lr, stop_eps, ntraining, ridge_alpha;
+    int ridge_in_grad;
+    const int32_t* fixed;   // P entries (1 = held fixed: params_optimization["index_fixed"]) or nullptr
+    double* theta;          // current hyper-parameters (read by the evaluation, advanced here)
+    const double* nll;      // likelihood value and gradient of the evaluation just finished
+    const double* grad;
+    double *m, *v;          // Adam moments
+    double* prev_loss;
+    int32_t* istate;        // [0] t, [1] converged once, [2] status (0 running), [3] iterations done
+    double *theta_hist, *loss_hist, *norm_hist;
+};
+__global__ void k_adam_step(AdamArgs a) {
+    const int i = threadIdx.x;
+    const int t = a.istate[0];
+    if (a.istate[2] != 0 || t >= a.max_iter) return;
+    const bool on = i < a.P;
+    const double th = on ? a.theta[i] : 0.0;
+    const double e2 = on ? exp(2.0 * th) : 0.0;
+    double s_th = th, s_e2 = e2;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s_th += __shfl_xor_sync(0xffffffffu, s_th, o);
+        s_e2 += __shfl_xor_sync(0xffffffffu, s_e2, o);
+    }
+    // logposterior = NLL + sum(theta) [+ ridge_alpha sum exp(theta)^2] (sub_modules/loss_modules.py:5-13), divided by the
+    // number of training points (optimizers.py:136-139); gradient: +1 per component (GP/gp.py:491-493)
+    const double value = (*a.nll + s_th + a.ridge_alpha * s_e2) / a.ntraining;
+    double g = 0.0;
+    if (on && !(a.fixed && a.fixed[i])) g = (a.grad[i] + 1.0 + (a.ridge_in_grad ? 2.0 * a.ridge_alpha * e2 : 0.0)) / a.ntraining;
+    const unsigned nan_g = __ballot_sync(0xffffffffu, g != g);
+    if (t == 0 && value != value) {  // "loss is nan at the initial hyper-parameters" (optimizers.py:245-246)
+        if (i == 0) { a.istate[2] = 4; a.loss_hist[0] = value; }
+        return;
+    }
+    if (nan_g) {                     // "gradient of loss became nan" (optimizers.py:182-183)
+        if (i == 0) a.istate[2] = 2;
+        return;
+    }
+    double g2 = g * g;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) g2 += __shfl_xor_sync(0xffffffffu, g2, o);
+    double th_new = th;
+    if (on) {
+        // optax.adam defaults: b1 = 0.9, b2 = 0.999, eps = 1e-8, eps_root = 0
+        const double b1 = 0.9, b2 = 0.999;
+        const double m = b1 * a.m[i] + (1.0 - b1) * g;
+        const double v = b2 * a.v[i] + (1.0 - b2) * g * g;
+        a.m[i] = m;
+        a.v[i] = v;
+        const double mhat = m / (1.0 - pow(b1, (double)(t + 1))), vhat = v / (1.0 - pow(b2, (double)(t + 1)));
+        th_new = th - a.lr * mhat / (sqrt(vhat) + 1e-8);
+        a.theta[i] = th_new;
+        a.theta_hist[(int64_t)(t + 1) * a.P + i] = th_new;
+    }
+    const unsigned nan_th = __ballot_sync(0xffffffffu, th_new != th_new);
+    if (i == 0) {
+        if (t == 0) a.loss_hist[0] = value;  // "loss before optimize": the same evaluation (optimizers.py:239-244)
+        a.loss_hist[t + 1] = value;
+        a.norm_hist[t] = sqrt(g2);
+        int status = 0, once = a.istate[1];
+        if (t >= 1) {                         // two-in-a-row plateau rule and divergence guard (optimizers.py:218-233)
+            if (fabs(value - *a.prev_loss) < a.stop_eps) {
+                if (once) status = 1; else once = 1;
+            } else if (nan_th) {
+                status = 3;
+            } else {
+                once = 0;
+            }
+        }
+        *a.prev_loss = value;
+        a.istate[0] = t + 1;
+        a.istate[1] = once;
+        a.istate[2] = status;
+        a.istate[3] = t + 1;
+    }
+}
+
 }  // namespace pigp
 
 using namespace pigp;
@@ -130,7 +210,7 @@ struct pigp_solver {
     int32_t* info = nullptr;
     // posterior workspace (allocated on first use, grow-only)
     double* V = nullptr;     // mpad x npad: K_ab -> K_ab L^-T
-    int64_t v_rows = 0;
+    int64_t v_elems = 0;
     double* T = nullptr;     // mpad x mpad test covariance (full posterior covariance only)
     int64_t t_elems = 0;
     double* kdiag = nullptr; // diag(K_aa)
@@ -437,6 +517,7 @@ static int trsm_rec(double* V, int64_t ldv, int64_t m, const FactorView& f, int 
         g.B = f.invd + (int64_t)c0 * TILE * TILE; g.ldb = TILE; g.b_kcontig = 1;
         g.C = V + (int64_t)c0 * TILE; g.ldc = ldv;
         g.force_bn128 = 1;  // in place: a CTA reads its 128 columns of its rows before it writes them
+        g.Lkk = f.L + (int64_t)c0 * TILE * f.ld + (int64_t)c0 * TILE; g.ldl = f.ld;  // refined (see k_trsm_refine)
         return launch_gemm(g, st);
     }
     const int n1 = nt / 2, n2 = nt - n1;
@@ -504,7 +585,7 @@ int pigp_predict(pigp_solver* s, const pigp_plan* mixed, const pigp_plan* test, 
     cudaStream_t st = as_stream(stream);
     int32_t* info = info_dev ? info_dev : s->info;
     const int64_t m = mixed->rows, mpad = round_up(m, TILE), ld = s->npad;
-    PIGP_TRY(grow(&s->V, &s->v_rows, mpad));
+    PIGP_TRY(grow(&s->V, &s->v_elems, mpad * ld));
     // L and L^-1 y from the solver's own factorisation (the NLL value is a by-product, parked in d_res)
     PIGP_TRY(pigp_dsolver_nll_grad(s->ds, theta_dev, y_dev, eps, s->d_res, nullptr, info, stream));
     const FactorView f = factor_view(s->ds);
@@ -570,6 +651,72 @@ int pigp_predict_batch_host(pigp_solver* s, pigp_plan* mixed, pigp_plan* test, i
     PIGP_CUDA(cudaMemcpy(cov_host, s->d_cov, sizeof(double) * cov_each * n_theta, cudaMemcpyDeviceToHost));
     if (info_host && n_theta == 1) *info_host = worst;
     return PIGP_OK;
+}
+
+int pigp_adam_host(pigp_solver* s, const double* theta0_host, const double* y_host, double eps, int max_iter, double lr,
+                   double stop_eps, double ntraining, double ridge_alpha, int ridge_in_grad, const int32_t* fixed_host,
+                   int check_every, double* theta_hist_host, double* loss_hist_host, double* norm_hist_host,
+                   int32_t* n_done_host, int32_t* status_host) {
+    if (!s || !theta0_host || !y_host || !theta_hist_host || !loss_hist_host || !norm_hist_host || !n_done_host || !status_host ||
+        max_iter < 1 || !(ntraining > 0.0)) {
+        set_error("pigp_adam_host: bad argument");
+        return PIGP_EINVAL;
+    }
+    PIGP_TRY(use_device(s->plan));
+    const int P = s->plan->theta_len;
+    if (check_every < 1) check_every = 16;
+    // workspace: [theta | m | v | nll | grad | prev_loss] doubles, histories, integer state, mask
+    const size_t n_d = (size_t)4 * MAX_THETA + 2 + (size_t)(max_iter + 1) * P + (size_t)(max_iter + 1) + (size_t)max_iter;
+    double* ws = nullptr;
+    int32_t* iws = nullptr;
+    PIGP_CUDA(cudaMalloc(&ws, sizeof(double) * n_d));
+    if (cudaMalloc(&iws, sizeof(int32_t) * (4 + MAX_THETA)) != cudaSuccess) { cudaFree(ws); set_error("pigp_adam_host: out of memory"); return PIGP_ENOMEM; }
+    int rc = PIGP_OK;
+    auto ck = [&](cudaError_t e) { if (e != cudaSuccess && rc == PIGP_OK) { set_error(std::string("pigp_adam_host: ") + cudaGetErrorString(e)); rc = PIGP_ECUDA; } };
+    ck(cudaMemset(ws, 0, sizeof(double) * n_d));
+    ck(cudaMemset(iws, 0, sizeof(int32_t) * (4 + MAX_THETA)));
+    AdamArgs a{};
+    a.P = P; a.max_iter = max_iter; a.lr = lr; a.stop_eps = stop_eps; a.ntraining = ntraining;
+    a.ridge_alpha = ridge_alpha; a.ridge_in_grad = ridge_in_grad;
+    a.theta = ws; a.m = ws + MAX_THETA; a.v = ws + 2 * MAX_THETA;
+    double* d_nll = ws + 3 * MAX_THETA;           // nll followed by the gradient
+    a.nll = d_nll; a.grad = d_nll + 1;
+    a.prev_loss = ws + 4 * MAX_THETA + 1;
+    a.theta_hist = ws + 4 * MAX_THETA + 2;
+    a.loss_hist = a.theta_hist + (size_t)(max_iter + 1) * P;
+    a.norm_hist = a.loss_hist + (max_iter + 1);
+    a.istate = iws;
+    a.fixed = fixed_host ? iws + 4 : nullptr;
+    ck(cudaMemcpy(a.theta, theta0_host, sizeof(double) * P, cudaMemcpyHostToDevice));
+    ck(cudaMemcpy(a.theta_hist, theta0_host, sizeof(double) * P, cudaMemcpyHostToDevice));
+    ck(cudaMemcpy(s->d_y, y_host, sizeof(double) * s->n, cudaMemcpyHostToDevice));
+    if (fixed_host) ck(cudaMemcpy(iws + 4, fixed_host, sizeof(int32_t) * P, cudaMemcpyHostToDevice));
+    int32_t ist[4] = {0, 0, 0, 0};
+    // theta never leaves the device: evaluation and update are enqueued back to back, the host looks at the state only
+    // every check_every iterations (a plateau found in between leaves the remaining queued updates as no-ops)
+    for (int it = 0; it < max_iter && rc == PIGP_OK && ist[2] == 0; it += check_every) {
+        const int nk = std::min(check_every, max_iter - it);
+        for (int k = 0; k < nk && rc == PIGP_OK; ++k) {
+            rc = pigp_dsolver_nll_grad(s->ds, a.theta, s->d_y, eps, d_nll, d_nll + 1, s->info, nullptr);
+            if (rc == PIGP_OK) {
+                k_adam_step<<<1, 32>>>(a);
+                count_launch();
+                ck(cudaGetLastError());
+            }
+        }
+        ck(cudaMemcpy(ist, iws, sizeof(ist), cudaMemcpyDeviceToHost));
+    }
+    if (rc == PIGP_OK) {
+        const int done = ist[3];
+        ck(cudaMemcpy(theta_hist_host, a.theta_hist, sizeof(double) * (size_t)(done + 1) * P, cudaMemcpyDeviceToHost));
+        ck(cudaMemcpy(loss_hist_host, a.loss_hist, sizeof(double) * (size_t)(done + 1), cudaMemcpyDeviceToHost));
+        if (done > 0) ck(cudaMemcpy(norm_hist_host, a.norm_hist, sizeof(double) * (size_t)done, cudaMemcpyDeviceToHost));
+        *n_done_host = done;
+        *status_host = ist[2];
+    }
+    cudaFree(ws);
+    cudaFree(iws);
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ building blocks

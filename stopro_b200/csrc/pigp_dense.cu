@@ -398,6 +398,138 @@ static int launch_gemm_small(const GemmDesc& d, cudaStream_t st) {
     return PIGP_OK;
 }
 
+// ----------------------------------------------------------------------------------------------- refined TRSM
+// X = A inv(Lkk)^T for 32-row slabs of a 128-column panel, in place, with one step of iterative refinement:
+//   X0 = A W^T,  R = A - X0 Lkk^T,  X = X0 + R W^T      (W = inv(Lkk) from k_potf2, B operand of the descriptor).
+// The explicit inverse of an ill-conditioned diagonal tile only satisfies |W Lkk - I| ~ n u cond(Lkk); one refinement
+// step squares that residual, which restores the row-wise backward stability of a substitution-based TRSM
+// (LAPACK-grade factorisation: backward error ~1e-16 instead of ~1e-13 on the cond(K) = 1e10 sinusoidal matrix).
+// One CTA per slab: the slab lives in shared memory for the three products, W / Lkk stream through a cp.async pipeline.
+constexpr int TR_BM = 32, TR_SLD = 128 + 8, TR_STAGES = 3;
+constexpr int TR_SMEM = (2 * TR_BM * TR_SLD + TR_STAGES * 128 * LDS_K) * (int)sizeof(double);
+
+__device__ __forceinline__ void trsm_stage(const double* S, const double* Bg, int64_t ldb, double* sB, double (&acc)[2][4][2],
+                                           int tid, int wm, int wn, int gid, int tig) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    constexpr int NK = 128 / BK, OPB = 128 * LDS_K;
+#pragma unroll
+    for (int s = 0; s < TR_STAGES - 1; ++s) {
+        load_operand<true, 128, 256>(sB + s * OPB, Bg, ldb, 0, (int64_t)s * BK, tid);
+        cp_async_commit();
+    }
+    for (int it = 0; it < NK; ++it) {
+        cp_async_wait<TR_STAGES - 2>();
+        __syncthreads();
+        {
+            const int nx = it + TR_STAGES - 1;
+            if (nx < NK) load_operand<true, 128, 256>(sB + (nx % TR_STAGES) * OPB, Bg, ldb, 0, (int64_t)nx * BK, tid);
+            cp_async_commit();
+        }
+        const double* b = sB + (it % TR_STAGES) * OPB;
+#pragma unroll
+        for (int k8 = 0; k8 < BK; k8 += 8) {
+            double2 af[2], bf[4];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+                af[mi] = *reinterpret_cast<const double2*>(S + (wm * 16 + 8 * mi + gid) * TR_SLD + it * BK + k8 + 2 * tig);
+            load_frags<true, 4, 128>(bf, b, wn * 32, k8, gid, tig);
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi].x, bf[ni].x);
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi].y, bf[ni].y);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();  // every warp is done with S and the pipeline buffers
+}
+
+__global__ void __launch_bounds__(256) k_trsm_refine(GemmDesc g) {
+    extern __shared__ __align__(16) double smem[];
+    double* S0 = smem;                       // A, later the residual R
+    double* S1 = S0 + TR_BM * TR_SLD;        // X0
+    double* sB = S1 + TR_BM * TR_SLD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int wm = warp & 1, wn = warp >> 1;
+    constexpr int SUB = BM / TR_BM;
+    const int tm = blockIdx.x;
+    const int64_t m0 = (int64_t)(tm / SUB) * g.m_ts * BM + (tm % SUB) * TR_BM;
+    wait_flags(g, tid);
+    // slab -> S0 (16-byte asynchronous copies)
+    for (int c = tid; c < TR_BM * 64; c += 256) {
+        const int r = c >> 6, j2 = (c & 63) * 2;
+        cp_async16(S0 + r * TR_SLD + j2, g.A + (m0 + r) * g.lda + j2);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    double acc[2][4][2];
+    // X0 = A W^T -> S1
+    trsm_stage(S0, g.B, g.ldb, sB, acc, tid, wm, wn, gid, tig);
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            double* row = S1 + (wm * 16 + 8 * mi + gid) * TR_SLD + wn * 32 + 16 * q + 2 * tig;
+            *reinterpret_cast<double2*>(row) = make_double2(acc[mi][2 * q][0], acc[mi][2 * q][1]);
+            *reinterpret_cast<double2*>(row + 8) = make_double2(acc[mi][2 * q + 1][0], acc[mi][2 * q + 1][1]);
+        }
+    __syncthreads();
+    // R = A - X0 Lkk^T -> S0
+    trsm_stage(S1, g.Lkk, g.ldl, sB, acc, tid, wm, wn, gid, tig);
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            double* row = S0 + (wm * 16 + 8 * mi + gid) * TR_SLD + wn * 32 + 16 * q + 2 * tig;
+            double2 a0 = *reinterpret_cast<double2*>(row), a1 = *reinterpret_cast<double2*>(row + 8);
+            a0.x -= acc[mi][2 * q][0]; a0.y -= acc[mi][2 * q][1];
+            a1.x -= acc[mi][2 * q + 1][0]; a1.y -= acc[mi][2 * q + 1][1];
+            *reinterpret_cast<double2*>(row) = a0;
+            *reinterpret_cast<double2*>(row + 8) = a1;
+        }
+    __syncthreads();
+    // X = X0 + R W^T -> global (in place)
+    trsm_stage(S0, g.B, g.ldb, sB, acc, tid, wm, wn, gid, tig);
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int lr = wm * 16 + 8 * mi + gid, lc = wn * 32 + 16 * q + 2 * tig;
+            const double2 x0 = *reinterpret_cast<const double2*>(S1 + lr * TR_SLD + lc);
+            const double2 x1 = *reinterpret_cast<const double2*>(S1 + lr * TR_SLD + lc + 8);
+            double* out = g.C + (m0 + lr) * g.ldc + lc;
+            *reinterpret_cast<double2*>(out) = make_double2(x0.x + acc[mi][2 * q][0], x0.y + acc[mi][2 * q][1]);
+            *reinterpret_cast<double2*>(out + 8) = make_double2(x1.x + acc[mi][2 * q + 1][0], x1.y + acc[mi][2 * q + 1][1]);
+        }
+}
+
+static int launch_trsm_refine(const GemmDesc& d, cudaStream_t st) {
+    static bool attr_done[64] = {};
+    int dev = 0;
+    PIGP_CUDA(cudaGetDevice(&dev));
+    if (!attr_done[dev & 63]) {
+        PIGP_CUDA(cudaFuncSetAttribute(k_trsm_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
+        attr_done[dev & 63] = true;
+    }
+    double flops = 0.0;
+    if (g_prof_on) {
+        flops = 3.0 * 2.0 * d.M * 128.0 * 128.0;
+        prof_note(d.M, d.N, d.K, 200);
+    }
+    ProfScope prof(PROF_GEMM, st, flops);
+    k_trsm_refine<<<(unsigned)(d.M / TR_BM), 256, TR_SMEM, st>>>(d);
+    count_launch();
+    return PIGP_OK;
+}
+
 static int g_gemm_bn = 0;  // 0: read PIGP_GEMM_BN once (kernel tuning); 128 or 64
 
 template <int BN_, int STAGES_>
@@ -446,6 +578,15 @@ int launch_gemm(const GemmDesc& g_in, cudaStream_t st) {
         return PIGP_EINVAL;
     }
     if (g.m_ts == 0) g.m_ts = 1;
+    if (g.Lkk) {
+        if (g.N != BM || g.K != BM || !g.a_kcontig || !g.b_kcontig || g.C != g.A || g.alpha != 1.0 || g.beta != 0.0) {
+            set_error("pigp gemm: the refined TRSM is in place with N = K = 128 and k-contiguous operands");
+            return PIGP_EINVAL;
+        }
+        PIGP_TRY(launch_trsm_refine(g, st));
+        PIGP_CUDA(cudaGetLastError());
+        return PIGP_OK;
+    }
     if (g.lower_only && !g.gen && g.M < g.N) { set_error("pigp gemm: lower_only needs M >= N"); return PIGP_EINVAL; }
     if (g_gemm_bn == 0) {
         const char* e = getenv("PIGP_GEMM_BN");
@@ -768,6 +909,7 @@ static int chol_rec(double* A, int64_t ld, int64_t n, int64_t m_below, double* i
             g.B = invd; g.ldb = TILE; g.b_kcontig = 1;
             g.C = A + TILE * ld; g.ldc = ld;
             g.force_bn128 = 1;
+            g.Lkk = A; g.ldl = ld;
             PIGP_TRY(launch_gemm(g, st));
         }
         return PIGP_OK;
@@ -975,6 +1117,8 @@ int preload_dense() {
     PIGP_CUDA(cudaFuncSetAttribute(k_gemm_s<64, 64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (64 + 64) * LDS_K * (int)sizeof(double)));
     PIGP_PRELOAD((k_gemm_s<32, 128, 3>));
     PIGP_PRELOAD((k_gemm_s<64, 64, 3>));
+    PIGP_CUDA(cudaFuncSetAttribute(k_trsm_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
+    PIGP_PRELOAD(k_trsm_refine);
     PIGP_TRY((gemm_attrs<128, 4>()));
     PIGP_TRY((gemm_attrs<64, 3>()));
     PIGP_CUDA(cudaFuncSetAttribute(k_potf2, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM));

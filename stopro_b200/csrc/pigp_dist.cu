@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(256) k_push_panel(const double* L, int64_t ld,
     }
     push_done(sg);
 }
-// inverse diagonal tile (lower triangle) and the diagonal of L_kk (all the peers read of it: the log-det); 8 CTAs
+// inverse diagonal tile (lower triangle) and L_kk itself (full tile, zeros above the diagonal: the peers' refined TRSMs
+// multiply by it, and their log-det reads its diagonal); 8 CTAs
 struct PeerDiag { int n; double* invd[7]; double* lkk[7]; };
 __global__ void __launch_bounds__(256) k_push_diag(const double* invk, const double* Lkk, int64_t ld, PeerDiag pd, PushSig sg) {
     const int r0 = blockIdx.x * 16;
@@ -106,11 +107,8 @@ __global__ void __launch_bounds__(256) k_push_diag(const double* invk, const dou
             const double2 v = *reinterpret_cast<const double2*>(invk + i * 128 + j2);
             for (int p = 0; p < pd.n; ++p) *reinterpret_cast<double2*>(pd.invd[p] + i * 128 + j2) = v;
         }
-    }
-    if (threadIdx.x < 16) {
-        const int i = r0 + threadIdx.x;
-        const double v = Lkk[(int64_t)i * ld + i];
-        for (int p = 0; p < pd.n; ++p) pd.lkk[p][(int64_t)i * ld + i] = v;
+        const double2 l = *reinterpret_cast<const double2*>(Lkk + (int64_t)i * ld + j2);
+        for (int p = 0; p < pd.n; ++p) *reinterpret_cast<double2*>(pd.lkk[p] + (int64_t)i * ld + j2) = l;
     }
     push_done(sg);
 }
@@ -406,6 +404,7 @@ int leaf(const Ctx& c, int k) {
             g.C = Cb; g.ldc = ld;
             g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = k; g.k_gt0 = k;
             g.force_bn128 = 1;  // in place
+            g.Lkk = Akk; g.ldl = ld;  // refined: needs L_kk itself next to its inverse (peers receive both)
             if (!mine) PIGP_TRY(set_wait_one(c, g, s->f_diag(k), c.st));
             PIGP_TRY(launch_gemm(g, c.st));
         }

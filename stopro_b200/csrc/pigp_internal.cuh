@@ -144,6 +144,10 @@ struct GemmDesc {
     int n_gt0;       // global tile index (128 units) of column 0 of C
     int k_gt0;       // global tile index of k = 0 (kmode 1: k_tile >= gm, kmode 2: k_tile <= gm, in global tiles)
     int force_bn128; // one CTA per 128 x 128 tile (required when C aliases A: the CTA reads its rows before it writes them)
+    // ---- triangular solve by the inverse diagonal tile with one step of iterative refinement (N = K = 128, in place):
+    //      X0 = A W^T;  X = X0 + (A - X0 Lkk^T) W^T   with B = W = inv(Lkk).  |W Lkk - I| grows like n u cond(Lkk)
+    //      (1e-8 for the eps = 1e-6 Stokes matrices); the refinement step brings the panel back to substitution quality.
+    const double* Lkk; int64_t ldl;
     // ---- stores mirrored into peer memory (NVLink P2P) for row tiles with gm < push_gm_end
     int npeers;
     int push_gm_end;

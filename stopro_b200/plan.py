@@ -223,6 +223,30 @@ class Solver:
     def nll(self, theta_ptr, y_ptr, eps, nll_ptr, info_ptr=None, stream=None):
         _lib.check(_lib.lib().pigp_nll(self.handle, theta_ptr, y_ptr, float(eps), nll_ptr, info_ptr, stream))
 
+    def adam_host(self, theta0, y, eps, max_iter, lr, stop_eps, ntraining, ridge_alpha=0.0, ridge_in_grad=True, fixed=None,
+                  check_every=16):
+        """Device-resident optimize_by_adam loop (pigp_adam_host) -> (theta_hist (n+1, P), loss_hist (n+1,),
+        gradnorm_hist (n,), status)."""
+        p = self.plan
+        th = p._theta(theta0)
+        yy = np.ascontiguousarray(np.asarray(y, dtype=np.float64).ravel())
+        P = p.theta_len
+        theta_hist = np.empty((max_iter + 1, P), dtype=np.float64)
+        loss_hist = np.empty(max_iter + 1, dtype=np.float64)
+        norm_hist = np.empty(max_iter, dtype=np.float64)
+        mask = None
+        if fixed is not None and len(fixed):
+            mask = np.zeros(P, dtype=np.int32)
+            mask[np.asarray(fixed, dtype=int)] = 1
+        n_done, status = C.c_int32(), C.c_int32()
+        _lib.check(_lib.lib().pigp_adam_host(self.handle, th.ctypes.data, yy.ctypes.data, float(eps), int(max_iter), float(lr),
+                                             float(stop_eps), float(ntraining), float(ridge_alpha), int(ridge_in_grad),
+                                             mask.ctypes.data if mask is not None else None, int(check_every),
+                                             theta_hist.ctypes.data, loss_hist.ctypes.data, norm_hist.ctypes.data,
+                                             C.addressof(n_done), C.addressof(status)))
+        n = n_done.value
+        return theta_hist[:n + 1].copy(), loss_hist[:n + 1].copy(), norm_hist[:n].copy(), status.value
+
     def predict_host(self, mixed, test, theta, y, eps, full_cov=True):
         mu, cov, info = self.predict_batch_host(mixed, test, [theta], y, eps, full_cov=full_cov)
         return mu[0], cov[0], int(info[0])

@@ -5,7 +5,8 @@ as first loss entry and NaN guard (:239-246), the Adam update (optax.adam defaul
 eps = 1e-8), history lists of theta / loss / gradient norm, the two-in-a-row plateau stop on |delta loss| < eps
 (:224-229) and the NaN guards on gradient and theta (:182-183, :230-232).  What differs: value and gradient come from
 ONE factorisation (``f.value_and_grad`` of stopro_b200's logposterior) instead of func + dfunc assembling and
-factorising K twice per step (:148-150).  The optional scipy pre-stage is delegated to scipy.optimize.minimize.
+factorising K twice per step (:148-150); and when the loss is stopro_b200's logposterior over a GP model the whole loop
+runs on the device (``_device_loop`` -> pigp_adam_host), the host loop below being the fallback.  The optional scipy pre-stage is delegated to scipy.optimize.minimize.
 """
 import numpy as np
 
@@ -16,6 +17,38 @@ def _value_and_grad(f, df):
     if df is None:
         raise ValueError("a gradient function is required")
     return lambda p, *args: (f(p, *args), df(p, *args))
+
+
+def _device_loop(f, df, init, params_optimization, ntraining, index_fixed, args):
+    """The whole Adam loop on the device (pigp_adam_host) when the loss is stopro_b200's logposterior over a GP model:
+    theta, the moments and the histories stay in HBM, evaluation and update are enqueued back to back and the host only
+    looks at the stop flag every few iterations.  Same lists and exceptions as the host loop below.  Not used with a
+    scipy pre-stage, with print_process (per-step run.out lines) or with params_optimization["device_loop"] = False."""
+    model = getattr(f, "model", None)
+    if (model is None or not hasattr(model, "adam_device") or not params_optimization.get("device_loop", True)
+            or params_optimization.get("print_process", False) or not params_optimization.get("maxiter_GD")
+            or (params_optimization.get("maxiter_scipy") or [0])[0]):
+        return None
+    # jit(grad(func)) differentiates the ridge term; the explicit-derivative scripts (df = gp.d_logposterior) drop it
+    explicit = getattr(df, "__func__", None) is getattr(type(model), "d_logposterior", None) and df is not None
+    out = model.adam_device(init, *args, max_iter=params_optimization["maxiter_GD"], lr=params_optimization["lr"],
+                            stop_eps=params_optimization["eps"], ntraining=ntraining,
+                            ridge_alpha=getattr(f, "ridge_alpha", 0.0), ridge_in_grad=not explicit, fixed=index_fixed or None)
+    if out is None:
+        return None
+    theta_hist, loss_hist, norms, status = out
+    print(f"loss before optimize: {loss_hist[0]}")
+    if status == 4:
+        raise Exception("loss is nan at the initial hyper-parameters")
+    if status == 2:
+        raise Exception("gradient of loss became nan")
+    if status == 3:
+        print("diverged")
+        raise Exception("theta became nan")
+    if status == 1:
+        print("converged")
+    theta = [t.copy() for t in theta_hist]
+    return theta[-1], [float(v) for v in loss_hist], theta, [float(v) for v in norms]
 
 
 def optimize_by_adam(f, df, hf, init, params_optimization, *args):
@@ -31,8 +64,11 @@ def optimize_by_adam(f, df, hf, init, params_optimization, *args):
 
     r_train = args[0]
     ntraining = sum(np.shape(r)[0] for r in r_train)
-    vg = _value_and_grad(f, df)
     init = np.asarray(init, dtype=np.float64).copy()
+    device = _device_loop(f, df, init, params_optimization, ntraining, index_fixed, args)
+    if device is not None:
+        return device
+    vg = _value_and_grad(f, df)
     free = np.ones(len(init), dtype=bool)
     if index_fixed:
         free[np.asarray(index_fixed, dtype=int)] = False
