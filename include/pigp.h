@@ -26,6 +26,8 @@
  *   PIGP_SIDE_CHUNK=<t>   issue the side stream's products in k-chunks of t tiles
  *   PIGP_FUSE_WAITS=1     spin on the DIAG flag inside the consuming TRSM instead of a one-CTA wait kernel
  *   PIGP_PROF_DUMP=<csv>  per-launch timeline written by pigp_profile_stop
+ *   PIGP_LOOKAHEAD=<W>    panel schedule with look-ahead, W tile columns per panel (see pigp_set_lookahead)
+ *   PIGP_WAIT_TIMEOUT_S / PIGP_BARRIER_TIMEOUT_S   flag-wait limits of the multi-GPU path (see pigp_dsolver_reset)
  */
 #ifndef PIGP_H
 #define PIGP_H
@@ -36,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PIGP_ABI_VERSION 1
+#define PIGP_ABI_VERSION 2
 #define PIGP_MAX_TERMS 8   /* monomials per block (3-D Kfzfz needs 7) */
 #define PIGP_MAX_GROUPS 4  /* hyper-parameter groups per model (ux, uy, uz, pp); a block may use all of them */
 #define PIGP_TILE 128      /* row/column padding unit of every factorisation buffer */
@@ -90,7 +92,12 @@ typedef struct {
     double lbox[3];         /* periodic shift vector (self.lbox) */
     int32_t noise_lo_block; /* index_optimize_noise[0], or -1: plain jitter (GP/gp.py:23-42) */
     int32_t noise_hi_block; /* index_optimize_noise[-1]: diagonal add-on is 1 before the range, exp(noise) inside, eps after (GP/gp.py:44-70) */
+    int32_t kernel_type;    /* params_model["kernel_type"] (GP/kernels.py:331-427): PIGP_KERNEL_SE, or PIGP_KERNEL_MT52 / _MT72 /
+                               _MT92 = the Matern kernels of GP/kernels.py:127-205, G_n then being the n-th derivative of
+                               q(rho) exp(-rho), rho = kappa |s| / l, with the reference's autodiff value 0 at s = 0 for n >= 1 */
+    int32_t reserved;
 } pigp_plan_desc;
+enum { PIGP_KERNEL_SE = 0, PIGP_KERNEL_MT52 = 52, PIGP_KERNEL_MT72 = 72, PIGP_KERNEL_MT92 = 92 };
 
 typedef struct pigp_plan pigp_plan;
 typedef struct pigp_solver pigp_solver;
@@ -242,6 +249,10 @@ int64_t pigp_launch_count(void);
 /* on = 1 (default): the Y = L^-T products run on a side stream concurrently with the Cholesky chain.  on = 0 puts every
  * kernel on one stream, so that per-launch event times do not overlap (used by the per-class timing pass of bench.py). */
 int pigp_set_side_stream(int on);
+/* Panel schedule of the factorisation: tiles = 0 is the plain recursion; tiles = W > 0 factors coarse panels of W tile
+ * columns on the chain stream and applies each panel to the rest of the matrix on a bulk stream, one panel ahead (the big
+ * trailing updates leave the N/128-step dependency chain).  Default: PIGP_LOOKAHEAD, else 0.  Process-global. */
+int pigp_set_lookahead(int tiles);
 int pigp_profile_start(void);
 int pigp_profile_stop(double* ms_out, int64_t* launches_out, double* flops_out);
 

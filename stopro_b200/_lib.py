@@ -11,6 +11,8 @@ MAX_GROUPS = 4
 TILE = 128
 LAYOUT_FULL, LAYOUT_LOWER = 0, 1
 IPC_HANDLE_BYTES = 64
+ABI_VERSION = 2
+KERNEL_TYPES = {"se": 0, "mt52": 52, "mt72": 72, "mt92": 92}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PIGP_LIB") or os.path.join(_HERE, "libpigp.so")  # PIGP_LIB: alternate build (kernel tuning only)
@@ -31,7 +33,8 @@ class PlanDesc(C.Structure):
                 ("sec_row", C.POINTER(C.c_int64)), ("sec_col", C.POINTER(C.c_int64)),
                 ("pts_row_host", C.POINTER(C.c_double)), ("pts_col_host", C.POINTER(C.c_double)),
                 ("table", C.POINTER(BlockDesc)), ("lbox", C.c_double * 3),
-                ("noise_lo_block", C.c_int32), ("noise_hi_block", C.c_int32)]
+                ("noise_lo_block", C.c_int32), ("noise_hi_block", C.c_int32), ("kernel_type", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class PigpError(RuntimeError):
@@ -90,6 +93,7 @@ _SIGNATURES = {
     "pigp_dsolver_reset": (C.c_int, [C.c_void_p]),
     "pigp_launch_count": (C.c_int64, []),
     "pigp_set_side_stream": (C.c_int, [C.c_int]),
+    "pigp_set_lookahead": (C.c_int, [C.c_int]),
     "pigp_debug_potf2_stamps": (C.c_int, [C.c_void_p]),
     "pigp_profile_start": (C.c_int, []),
     "pigp_profile_stop": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -109,7 +113,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.pigp_abi_version() != 1:
+        if handle.pigp_abi_version() != ABI_VERSION:
             raise PigpError("libpigp.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -321,6 +321,7 @@ int pigp_plan_create(const pigp_plan_desc* d, pigp_plan** out) {
     for (int k = 0; k < 3; ++k) p->lbox[k] = d->lbox[k];
     p->noise_lo_block = d->noise_lo_block;
     p->noise_hi_block = d->noise_hi_block;
+    p->kernel_type = d->kernel_type;
     p->theta_len = d->n_groups * (1 + d->dim);
     auto fail = [&](const char* msg) {
         set_error(msg);
@@ -331,6 +332,9 @@ int pigp_plan_create(const pigp_plan_desc* d, pigp_plan** out) {
         if (p->sec_row[i + 1] < p->sec_row[i]) return fail("pigp_plan_create: sec_row must be non-decreasing");
     for (size_t i = 0; i + 1 < p->sec_col.size(); ++i)
         if (p->sec_col[i + 1] < p->sec_col[i]) return fail("pigp_plan_create: sec_col must be non-decreasing");
+    if (p->kernel_type != PIGP_KERNEL_SE && p->kernel_type != PIGP_KERNEL_MT52 && p->kernel_type != PIGP_KERNEL_MT72 &&
+        p->kernel_type != PIGP_KERNEL_MT92)
+        return fail("pigp_plan_create: unknown kernel_type");
     if (p->rows <= 0 || p->cols <= 0 || p->rows > (1 << 30) || p->cols > (1 << 30))
         return fail("pigp_plan_create: empty or oversized matrix");
     if (p->noise_lo_block >= 0) {

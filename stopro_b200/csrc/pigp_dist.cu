@@ -268,11 +268,9 @@ struct pigp_dsolver {
     cudaStream_t sa = nullptr, sb = nullptr, sc = nullptr;  // sc: publication kernels (peer stores), off the chain
     cudaEvent_t ev_in = nullptr, ev_bar = nullptr, ev_b = nullptr, ev_c = nullptr, ev_out = nullptr;
     std::vector<cudaEvent_t> ev_diag, ev_upd;
-#ifdef PIGP_EXPERIMENTAL_LOOKAHEAD
     cudaStream_t sd = nullptr;                // bulk trailing updates of the panel schedule
     std::vector<cudaEvent_t> ev_pan, ev_next; // per coarse panel: chain done / next panel's columns updated
     cudaEvent_t ev_d = nullptr;
-#endif
 
     int f_diag(int k) const { return k; }
     int f_panel(int k, int src) const { return T + k * world + src; }
@@ -510,17 +508,16 @@ int rec(const Ctx& c, int c0, int nt) {
     return rec(c, c0 + n1, n2);
 }
 
-#ifdef PIGP_EXPERIMENTAL_LOOKAHEAD
-// ---- EXPERIMENTAL (not compiled into the shipped library; round-2 work, never run on a GPU yet).
+// ---- Panel schedule with look-ahead (PIGP_LOOKAHEAD=<W tiles>; 0 = the plain recursion).
 // Coarse right-looking panels of W tile columns with the recursive factorisation inside a panel and a depth-1
 // look-ahead: the chain stream factors panel p (rec over its W columns, all own rows below), the bulk stream applies
 // panel p to the columns of panel p + 1 first (the chain waits only for that) and to the rest afterwards, concurrently
 // with the chain's work on panel p + 1.  The big trailing updates thereby leave the N/128-step dependency chain; the
 // L^-T products get the matching right-looking update V_p on the side stream.  Uses the existing kernels only.
+static int g_lookahead = -1;  // -1: read PIGP_LOOKAHEAD once; set by pigp_set_lookahead
 static int lookahead_width() {
-    static int w = -1;
-    if (w < 0) { const char* e = getenv("PIGP_LOOKAHEAD"); w = e ? std::max(0, atoi(e)) : 0; }
-    return w;
+    if (g_lookahead < 0) { const char* e = getenv("PIGP_LOOKAHEAD"); g_lookahead = e ? std::max(0, atoi(e)) : 0; }
+    return g_lookahead;
 }
 
 static int ensure_lookahead(pigp_dsolver* s) {
@@ -596,11 +593,11 @@ static int chol_lookahead(const Ctx& c, int W) {
     PIGP_CUDA(cudaStreamWaitEvent(c.st, s->ev_d, 0));
     return PIGP_OK;
 }
-#endif  // PIGP_EXPERIMENTAL_LOOKAHEAD
 
 int preload_dist() {
     PIGP_TRY(preload_dense());
     PIGP_TRY(preload_assemble());
+    PIGP_TRY(preload_matern());
     PIGP_PRELOAD(k_signal); PIGP_PRELOAD(k_wait); PIGP_PRELOAD(k_push_rows); PIGP_PRELOAD(k_place_diag_t);
     PIGP_PRELOAD(k_gemv_upper); PIGP_PRELOAD(k_set_ytile); PIGP_PRELOAD(k_push_vec); PIGP_PRELOAD(k_sum_slots);
     PIGP_PRELOAD(k_finish_nll_d); PIGP_PRELOAD(k_diag_info); PIGP_PRELOAD(k_copy_v); PIGP_PRELOAD(k_push_panel); PIGP_PRELOAD(k_push_diag);
@@ -620,12 +617,10 @@ void pigp_dsolver_destroy(pigp_dsolver* s) {
     if (s->sa) cudaStreamDestroy(s->sa);
     if (s->sb) cudaStreamDestroy(s->sb);
     if (s->sc) cudaStreamDestroy(s->sc);
-#ifdef PIGP_EXPERIMENTAL_LOOKAHEAD
     if (s->sd) cudaStreamDestroy(s->sd);
     if (s->ev_d) cudaEventDestroy(s->ev_d);
     for (cudaEvent_t e : s->ev_pan) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : s->ev_next) if (e) cudaEventDestroy(e);
-#endif
     for (cudaEvent_t e : {s->ev_in, s->ev_bar, s->ev_b, s->ev_c, s->ev_out}) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : s->ev_diag) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : s->ev_upd) if (e) cudaEventDestroy(e);
@@ -709,6 +704,11 @@ int pigp_dsolver_create(pigp_plan* plan, int rank, int world, pigp_dsolver** out
     if (rc != PIGP_OK) { pigp_dsolver_destroy(s); return rc; }
     s->connected = (world == 1);
     *out = s;
+    return PIGP_OK;
+}
+
+int pigp_set_lookahead(int tiles) {
+    g_lookahead = tiles < 0 ? 0 : tiles;
     return PIGP_OK;
 }
 
@@ -847,11 +847,8 @@ static int dsolver_enqueue(pigp_dsolver* s, const double* theta_dev, const doubl
         count_launch();
     }
     PIGP_CUDA(cudaGetLastError());
-#ifdef PIGP_EXPERIMENTAL_LOOKAHEAD
-    if (lookahead_width() > 0 && g_side_stream) PIGP_TRY(chol_lookahead(c, lookahead_width()));
-    else
-#endif
-    PIGP_TRY(rec(c, 0, s->T));
+    if (lookahead_width() > 0 && g_side_stream && s->T > lookahead_width()) PIGP_TRY(chol_lookahead(c, lookahead_width()));
+    else PIGP_TRY(rec(c, 0, s->T));
     if (c.npeers > 0) {
         // the diagonal of every L_kk (log-det) travels with the DIAG flags; a GEMM only waits for the flags it consumes
         ProfScope prof(PROF_MISC, st);

@@ -77,6 +77,7 @@ enum {
 
 struct pigp_plan {
     int dim = 0, product_form = 1, n_groups = 0, symmetric = 0;
+    int kernel_type = 0;  // 0 squared exponential; 52 / 72 / 92 Matern
     int n_row_blocks = 0, n_col_blocks = 0;
     std::vector<int64_t> sec_row, sec_col;
     int64_t rows = 0, cols = 0;
@@ -104,6 +105,43 @@ struct pigp_plan {
 };
 
 namespace pigp {
+
+// ---- arguments shared by the block evaluators (pigp_assemble.cu: squared exponential; pigp_matern.cu: Matern)
+struct AsmArgs {
+    const AsmTile* tiles;
+    const pigp_block_desc* table;
+    const double* pts_row;  // [DIM][n_row_pts]
+    const double* pts_col;  // [DIM][n_col_pts]
+    int64_t n_row_pts, n_col_pts;
+    const double* theta;
+    int n_groups;
+    int has_noise;      // theta[n_groups*(1+DIM)] is the noise parameter
+    int64_t noise_lo, noise_hi;
+    double eps;
+    int add_diag;
+    double lbox[3];
+    double* K;          // assembly output
+    int64_t ld;
+    // gradient-only
+    const double* X;    // K^-1, lower triangle
+    const double* alpha;
+    double* partials;   // [n_tiles][MAX_THETA]
+};
+
+AsmArgs make_args(const pigp_plan* p, const AsmTile* tiles, const double* theta, double eps, int add_diag);
+int launch_blocks_matern(const pigp_plan* p, const AsmArgs& a, int64_t n_tiles, bool grad, cudaStream_t st);
+int preload_matern();
+
+#ifdef __CUDACC__
+__device__ __forceinline__ double diag_addon(const AsmArgs& a, int64_t R, double noise_exp) {
+    // GP/gp.py:23-42 (_add_jiggle) and :44-70 (_add_jiggle_noise)
+    if (!a.has_noise) return a.eps;
+    if (R < a.noise_lo) return 1.0;
+    if (R < a.noise_hi) return noise_exp;
+    return a.eps;
+}
+
+#endif
 
 // ---- assembly / gradient (pigp_assemble.cu)
 int launch_assemble(const pigp_plan* p, const AsmTile* tiles, int64_t n_tiles, const double* theta_dev, double eps,

@@ -61,7 +61,7 @@ def test_library_exports_every_declared_symbol(built_lib):
         assert hasattr(built_lib, name), f"{name} is declared in include/pigp.h but not exported"
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     built_lib.pigp_abi_version.restype = ctypes.c_int
-    assert built_lib.pigp_abi_version() == 1
+    assert built_lib.pigp_abi_version() == _lib.ABI_VERSION
     built_lib.pigp_launch_count.restype = ctypes.c_int64
     assert built_lib.pigp_launch_count() == 0  # nothing has been launched: no compute without a GPU
 
