@@ -26,13 +26,14 @@ from . import blocks_ref, closed_form
 
 class GPRef:
     def __init__(self, table, kernel_form="product", dim=None, lbox=None, index_optimize_noise=None,
-                 backend="closed", dtype=np.float64):
+                 backend="closed", dtype=np.float64, kernel_type="se"):
         self.table = blocks_ref.TABLES[table]
         self.dim = self.table["dim"] if self.table["dim"] is not None else dim
         self.form = kernel_form if self.dim == 2 else "product"  # kernels.py:419-426: 3-D ignores kernel_form
         self.lbox = None if lbox is None else np.asarray(lbox, dtype=np.float64)
         self.index_optimize_noise = index_optimize_noise if index_optimize_noise else False
         self.backend = backend
+        self.kernel_type = kernel_type  # "se" or "mt52" / "mt72" / "mt92" (closed backend only; oracle/matern_ref.py)
         self.dtype = dtype  # np.longdouble: closed-form blocks in extended precision (oracle/extended.py); closed backend only
         self._ad = None
 
@@ -49,6 +50,9 @@ class GPRef:
 
     def _op_eval(self, op, r, rp, theta_g):
         if self.backend == "closed":
+            if self.kernel_type != "se":
+                from . import matern_ref
+                return matern_ref.eval_operator(self.kernel_type, op, r, rp, theta_g, self.form, self.dim)
             return closed_form.eval_operator(op, r, rp, theta_g, self.form, self.dim, dtype=self.dtype)
         torch, ad = self._autodiff()
         t = lambda x: x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x), dtype=torch.float64)
@@ -225,6 +229,9 @@ class GPRef:
                     idx = list(range(len(th)))[sl]
 
                     def base(a, b):
+                        if self.kernel_type != "se":
+                            from . import matern_ref
+                            return matern_ref.eval_operator(self.kernel_type, op, a, b, th[sl], self.form, self.dim, with_grad=True)[1]
                         return closed_form.eval_operator(op, a, b, th[sl], self.form, self.dim, with_grad=True, dtype=self.dtype)[1]
 
                     a, b, l = pts[i], pts[j], self.lbox

@@ -72,3 +72,24 @@ def eval_terms(kind, terms, r, rp, theta, dim, product, with_grad=False):
             for e in dims:
                 grad[g * (1 + dim) + 1 + e] += coef * gamma * dfac[e] * np.prod([fac[d] for d in dims if d != e] + [np.ones_like(s[0])], axis=0)
     return (out, grad) if with_grad else out
+
+
+def eval_operator(kind, name, r, rp, theta, form, dim, with_grad=False):
+    """Same contract as oracle.closed_form.eval_operator (one differential operator of GP/gp_2D.py / gp_3D.py applied to the
+    kernel of one hyper-parameter group), for a Matern kernel."""
+    from . import closed_form
+
+    terms = []
+    for coef, alpha, beta in closed_form.operator_polynomial(name, dim):
+        sign = coef * (-1.0) ** sum(beta)
+        order = tuple(a + b for a, b in zip(alpha, beta))
+        if form == "product":
+            terms.append((0, sign, order))
+        else:
+            active = [d for d in range(dim) if order[d] > 0]
+            if len(active) == 0:
+                terms += [(0, sign, tuple(0 if d == e else -1 for d in range(dim))) for e in range(dim)]
+            elif len(active) == 1:
+                terms.append((0, sign, tuple(order[d] if d == active[0] else -1 for d in range(dim))))
+    out = eval_terms(kind, terms, r, rp, np.asarray(theta, dtype=np.float64), dim, form == "product", with_grad=with_grad)
+    return out

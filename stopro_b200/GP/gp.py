@@ -37,6 +37,7 @@ class GPmodel:
         self.Kernel = Kernel
         self.dim = Kernel.input_dim
         self.product_form = Kernel.product_form
+        self.kernel_type = getattr(Kernel, "kernel_type", "se")
         self.index_optimize_noise = index_optimize_noise if index_optimize_noise else False
         self.lbox = None if lbox is None else np.asarray(lbox, dtype=np.float64)
         if self.system == "stokes":
@@ -111,18 +112,30 @@ class GPmodel:
         if len(names) != len(r_train):
             raise ValueError(f"{type(self).__name__} has {len(self.train_observables)} training blocks, got {len(r_train)} point sets")
         return self._plan("train", lambda: Plan(self.dim, self.product_form, self._fields, self._observables(names), r_train,
-                                                lbox=self.lbox, noise_blocks=self.index_optimize_noise or None), r_train)
+                                                lbox=self.lbox, noise_blocks=self.index_optimize_noise or None,
+                                                kernel_type=self.kernel_type), r_train)
 
     def _mixed_plan(self, r_test, r_train):
         tr = self.train_observables[:len(r_train)]
         te = self.test_observables[:len(r_test)]
         return self._plan("mixed", lambda: Plan(self.dim, self.product_form, self._fields, self._observables(te), r_test,
-                                                self._observables(tr), r_train, lbox=self.lbox), r_test, r_train)
+                                                self._observables(tr), r_train, lbox=self.lbox, kernel_type=self.kernel_type),
+                          r_test, r_train)
 
     def _test_plan(self, r_test):
         te = self.test_observables[:len(r_test)]
         return self._plan("test", lambda: Plan(self.dim, self.product_form, self._fields, self._observables(te), r_test,
-                                               lbox=self.lbox, zero_blocks=self.test_zero_blocks), r_test)
+                                               lbox=self.lbox, zero_blocks=self.test_zero_blocks, kernel_type=self.kernel_type),
+                          r_test)
+
+    def enable_distributed(self, process_group=None, on=True):
+        """Select the sharded solver after construction (the subclasses keep the reference's constructor signatures, so
+        the switch is this method or the STOPRO_B200_DISTRIBUTED environment variable -- never the YAML)."""
+        if self._solver is not None:
+            self._solver.close()
+            self._solver = None
+        self._distributed, self._group, self._cache = bool(on), process_group, None
+        return self
 
     def _rank_world(self):
         """(rank, world) of the sharded evaluation; (0, 1) unless ``distributed`` was asked for and a group is up."""
@@ -323,7 +336,8 @@ class GPmodel:
                 raise AttributeError(name) from None
 
             def block(r, rp, theta):
-                plan = Plan(self.dim, self.product_form, self._fields, [oa], [r], [ob], [rp], lbox=self.lbox)
+                plan = Plan(self.dim, self.product_form, self._fields, [oa], [r], [ob], [rp], lbox=self.lbox,
+                            kernel_type=self.kernel_type)
                 try:
                     return plan.assemble_host(np.asarray(theta, dtype=np.float64)[:self.n_kernel_theta])
                 finally:

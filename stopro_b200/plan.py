@@ -30,8 +30,9 @@ class Plan:
     """A block matrix  [cov(A_i(r_i), B_j(r'_j))]_{ij}  bound to its point sets."""
 
     def __init__(self, dim, product_form, fields, row_obs, row_pts, col_obs=None, col_pts=None, lbox=None,
-                 noise_blocks=None, zero_blocks=()):
+                 noise_blocks=None, zero_blocks=(), kernel_type="se"):
         self.dim, self.product_form, self.fields = dim, bool(product_form), list(fields)
+        self.kernel_type = kernel_type
         self.symmetric = col_obs is None
         self.row_obs, self.col_obs = list(row_obs), (list(row_obs) if col_obs is None else list(col_obs))
         self._rows, self.sec_row = stack_points(row_pts, dim)
@@ -55,6 +56,7 @@ class Plan:
         d = _lib.PlanDesc()
         d.dim, d.product_form, d.n_groups, d.symmetric = dim, int(self.product_form), len(self.fields), int(self.symmetric)
         d.n_row_blocks, d.n_col_blocks = nr, nc
+        d.kernel_type = _lib.KERNEL_TYPES[kernel_type]
         d.sec_row, d.sec_col = _ptr(self.sec_row, C.c_int64), _ptr(self.sec_col, C.c_int64)
         d.pts_row_host, d.pts_col_host = _ptr(self._rows), _ptr(self._cols)
         d.table = table

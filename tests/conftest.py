@@ -22,7 +22,8 @@ def oracle_for(cfg, backend="closed"):
 
     kw = cfg["model_kwargs"]
     gp = GPRef(cfg["model"], kernel_form=cfg["kernel"]["kernel_form"], dim=cfg["kernel"]["input_dim"],
-               lbox=kw.get("lbox"), index_optimize_noise=kw.get("index_optimize_noise"), backend=backend)
+               lbox=kw.get("lbox"), index_optimize_noise=kw.get("index_optimize_noise"), backend=backend,
+               kernel_type=cfg["kernel"].get("kernel_type", "se"))
     gp.set_constants(cfg["r_test"], cfg["mu_test"], cfg["r_train"], cfg["delta_y"], cfg["eps"])
     return gp
 

@@ -13,7 +13,7 @@ class FakePlan:
     created = []
 
     def __init__(self, dim, product_form, fields, row_obs, row_pts, col_obs=None, col_pts=None, lbox=None,
-                 noise_blocks=None, zero_blocks=()):
+                 noise_blocks=None, zero_blocks=(), kernel_type="se"):
         self.symmetric = col_obs is None
         self.row_pts = [np.array(p) for p in row_pts]
         self.col_pts = None if col_pts is None else [np.array(p) for p in col_pts]

@@ -132,8 +132,16 @@ def test_define_kernel_semantics():
     assert abs(k(r1, r2, th) - want) < 1e-15
     # the reference ignores kernel_form for 3-D inputs (kernels.py:419-426)
     assert define_kernel(dict(kernel_type="se", kernel_form="additive", input_dim=3, distance_func=False)).product_form
+    # Matern kernels of GP/kernels.py:127-205
+    m = define_kernel(dict(kernel_type="mt52", kernel_form="product", input_dim=2, distance_func=False))
+    rho = np.sqrt(5.0) * np.abs(r1 - r2) * np.exp(-th[1:])
+    want = np.exp(0.3) * np.prod((1.0 + rho + rho ** 2 / 3.0) * np.exp(-rho))
+    assert m.kernel_type == "mt52" and abs(m(r1, r2, th) - want) < 1e-15
+    assert define_kernel(dict(kernel_type="mt92", kernel_form="additive", input_dim=3, distance_func=False)).product_form
     with pytest.raises(NotImplementedError):
-        define_kernel(dict(kernel_type="mt52", kernel_form="product", input_dim=2, distance_func=False))
+        define_kernel(dict(kernel_type="rq", kernel_form="product", input_dim=2, distance_func=False))
+    with pytest.raises(NotImplementedError):
+        define_kernel(dict(kernel_type="mt52", kernel_form="product", input_dim=3, distance_func=False))
 
 
 class _FakeModel:
