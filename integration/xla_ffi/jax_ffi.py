@@ -2,12 +2,12 @@
 have JAX >= 0.4.31.  This image has no JAX: importing this module without it raises ImportError, nothing else in
 stopro_b200 depends on it, and the numpy + ctypes classes in stopro_b200.GP are the tested host side here.
 
-    from stopro_b200 import jax_ffi
+    import jax_ffi                       # this file, integration/xla_ffi/jax_ffi.py
     f = jax_ffi.make_training_function(gp_model, r_train, eps)     # replaces gp_model.trainingFunction_all
     loss = jax.jit(lambda th, dy: f(th, dy) + jnp.sum(th))          # logposterior (sub_modules/loss_modules.py:5-13)
     dloss = jax.jit(jax.grad(loss, 0))                              # as test/test_1_sinusoidal_direct_main.py:76-78
 
-The C++ handlers are csrc/pigp_xla_ffi.cc (`make -C stopro_b200/csrc ffi JAX_FFI_INCLUDE=...`).
+The C++ handlers are pigp_xla_ffi.cc next to this file (`make JAX_FFI_INCLUDE=...` here).
 """
 import ctypes
 import os

@@ -3,7 +3,7 @@
 //
 // NOT built by default: neither JAX nor its headers (xla/ffi/api/ffi.h) exist in this image or on the GPU box, so this
 // translation unit has never been compiled here.  Where JAX >= 0.4.31 is installed:
-//     make -C stopro_b200/csrc ffi JAX_FFI_INCLUDE=$(python -c "import jax.ffi; print(jax.ffi.include_dir())")
+//     make -C integration/xla_ffi JAX_FFI_INCLUDE=$(python -c "import jax.ffi; print(jax.ffi.include_dir())")
 // builds libpigp_xla_ffi.so next to libpigp.so; stopro_b200/jax_ffi.py registers the targets.  The handlers only
 // forward: every pigp_* entry point used here enqueues on the stream it is given and never synchronises, which is the
 // FFI contract.  Plans / solvers are created from Python (set_constants) and travel as int64 attributes.

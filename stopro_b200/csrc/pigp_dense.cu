@@ -399,19 +399,21 @@ static int launch_gemm_small(const GemmDesc& d, cudaStream_t st) {
 }
 
 // ----------------------------------------------------------------------------------------------- refined TRSM
-// X = A inv(Lkk)^T for 32-row slabs of a 128-column panel, in place, with one step of iterative refinement:
+// X = A inv(Lkk)^T for 64-row slabs of a 128-column panel, in place, with one step of iterative refinement:
 //   X0 = A W^T,  R = A - X0 Lkk^T,  X = X0 + R W^T      (W = inv(Lkk) from k_potf2, B operand of the descriptor).
 // The explicit inverse of an ill-conditioned diagonal tile only satisfies |W Lkk - I| ~ n u cond(Lkk); one refinement
 // step squares that residual, which restores the row-wise backward stability of a substitution-based TRSM
 // (LAPACK-grade factorisation: backward error ~1e-16 instead of ~1e-13 on the cond(K) = 1e10 sinusoidal matrix).
 // One CTA per slab: the slab lives in shared memory for the three products, W / Lkk stream through a cp.async pipeline.
-constexpr int TR_BM = 32, TR_SLD = 128 + 8, TR_STAGES = 3;
-constexpr int TR_SMEM = (2 * TR_BM * TR_SLD + TR_STAGES * 128 * LDS_K) * (int)sizeof(double);
+constexpr int TR_SLD = 128 + 8, TR_STAGES = 3;
+__host__ __device__ constexpr int tr_smem(int bm) { return (2 * bm * TR_SLD + TR_STAGES * 128 * LDS_K) * (int)sizeof(double); }
 
-__device__ __forceinline__ void trsm_stage(const double* S, const double* Bg, int64_t ldb, double* sB, double (&acc)[2][4][2],
+template <int TR_BM>
+__device__ __forceinline__ void trsm_stage(const double* S, const double* Bg, int64_t ldb, double* sB, double (&acc)[TR_BM / 16][4][2],
                                            int tid, int wm, int wn, int gid, int tig) {
+    constexpr int TR_MI = TR_BM / 16;
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < TR_MI; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     constexpr int NK = 128 / BK, OPB = 128 * LDS_K;
@@ -431,17 +433,17 @@ __device__ __forceinline__ void trsm_stage(const double* S, const double* Bg, in
         const double* b = sB + (it % TR_STAGES) * OPB;
 #pragma unroll
         for (int k8 = 0; k8 < BK; k8 += 8) {
-            double2 af[2], bf[4];
+            double2 af[TR_MI], bf[4];
 #pragma unroll
-            for (int mi = 0; mi < 2; ++mi)
-                af[mi] = *reinterpret_cast<const double2*>(S + (wm * 16 + 8 * mi + gid) * TR_SLD + it * BK + k8 + 2 * tig);
+            for (int mi = 0; mi < TR_MI; ++mi)
+                af[mi] = *reinterpret_cast<const double2*>(S + (wm * (TR_BM / 2) + 8 * mi + gid) * TR_SLD + it * BK + k8 + 2 * tig);
             load_frags<true, 4, 128>(bf, b, wn * 32, k8, gid, tig);
 #pragma unroll
-            for (int mi = 0; mi < 2; ++mi)
+            for (int mi = 0; mi < TR_MI; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi].x, bf[ni].x);
 #pragma unroll
-            for (int mi = 0; mi < 2; ++mi)
+            for (int mi = 0; mi < TR_MI; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi].y, bf[ni].y);
         }
@@ -450,7 +452,9 @@ __device__ __forceinline__ void trsm_stage(const double* S, const double* Bg, in
     __syncthreads();  // every warp is done with S and the pipeline buffers
 }
 
+template <int TR_BM>
 __global__ void __launch_bounds__(256) k_trsm_refine(GemmDesc g) {
+    constexpr int TR_MI = TR_BM / 16;
     extern __shared__ __align__(16) double smem[];
     double* S0 = smem;                       // A, later the residual R
     double* S1 = S0 + TR_BM * TR_SLD;        // X0
@@ -470,25 +474,25 @@ __global__ void __launch_bounds__(256) k_trsm_refine(GemmDesc g) {
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    double acc[2][4][2];
+    double acc[TR_MI][4][2];
     // X0 = A W^T -> S1
-    trsm_stage(S0, g.B, g.ldb, sB, acc, tid, wm, wn, gid, tig);
+    trsm_stage<TR_BM>(S0, g.B, g.ldb, sB, acc, tid, wm, wn, gid, tig);
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi)
+    for (int mi = 0; mi < TR_MI; ++mi)
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            double* row = S1 + (wm * 16 + 8 * mi + gid) * TR_SLD + wn * 32 + 16 * q + 2 * tig;
+            double* row = S1 + (wm * (TR_BM / 2) + 8 * mi + gid) * TR_SLD + wn * 32 + 16 * q + 2 * tig;
             *reinterpret_cast<double2*>(row) = make_double2(acc[mi][2 * q][0], acc[mi][2 * q][1]);
             *reinterpret_cast<double2*>(row + 8) = make_double2(acc[mi][2 * q + 1][0], acc[mi][2 * q + 1][1]);
         }
     __syncthreads();
     // R = A - X0 Lkk^T -> S0
-    trsm_stage(S1, g.Lkk, g.ldl, sB, acc, tid, wm, wn, gid, tig);
+    trsm_stage<TR_BM>(S1, g.Lkk, g.ldl, sB, acc, tid, wm, wn, gid, tig);
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi)
+    for (int mi = 0; mi < TR_MI; ++mi)
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            double* row = S0 + (wm * 16 + 8 * mi + gid) * TR_SLD + wn * 32 + 16 * q + 2 * tig;
+            double* row = S0 + (wm * (TR_BM / 2) + 8 * mi + gid) * TR_SLD + wn * 32 + 16 * q + 2 * tig;
             double2 a0 = *reinterpret_cast<double2*>(row), a1 = *reinterpret_cast<double2*>(row + 8);
             a0.x -= acc[mi][2 * q][0]; a0.y -= acc[mi][2 * q][1];
             a1.x -= acc[mi][2 * q + 1][0]; a1.y -= acc[mi][2 * q + 1][1];
@@ -497,12 +501,12 @@ __global__ void __launch_bounds__(256) k_trsm_refine(GemmDesc g) {
         }
     __syncthreads();
     // X = X0 + R W^T -> global (in place)
-    trsm_stage(S0, g.B, g.ldb, sB, acc, tid, wm, wn, gid, tig);
+    trsm_stage<TR_BM>(S0, g.B, g.ldb, sB, acc, tid, wm, wn, gid, tig);
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi)
+    for (int mi = 0; mi < TR_MI; ++mi)
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            const int lr = wm * 16 + 8 * mi + gid, lc = wn * 32 + 16 * q + 2 * tig;
+            const int lr = wm * (TR_BM / 2) + 8 * mi + gid, lc = wn * 32 + 16 * q + 2 * tig;
             const double2 x0 = *reinterpret_cast<const double2*>(S1 + lr * TR_SLD + lc);
             const double2 x1 = *reinterpret_cast<const double2*>(S1 + lr * TR_SLD + lc + 8);
             double* out = g.C + (m0 + lr) * g.ldc + lc;
@@ -511,12 +515,13 @@ __global__ void __launch_bounds__(256) k_trsm_refine(GemmDesc g) {
         }
 }
 
-static int launch_trsm_refine(const GemmDesc& d, cudaStream_t st) {
+template <int TR_BM>
+static int launch_trsm_refine_t(const GemmDesc& d, cudaStream_t st) {
     static bool attr_done[64] = {};
     int dev = 0;
     PIGP_CUDA(cudaGetDevice(&dev));
     if (!attr_done[dev & 63]) {
-        PIGP_CUDA(cudaFuncSetAttribute(k_trsm_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
+        PIGP_CUDA(cudaFuncSetAttribute(k_trsm_refine<TR_BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem(TR_BM)));
         attr_done[dev & 63] = true;
     }
     double flops = 0.0;
@@ -525,9 +530,15 @@ static int launch_trsm_refine(const GemmDesc& d, cudaStream_t st) {
         prof_note(d.M, d.N, d.K, 200);
     }
     ProfScope prof(PROF_GEMM, st, flops);
-    k_trsm_refine<<<(unsigned)(d.M / TR_BM), 256, TR_SMEM, st>>>(d);
+    k_trsm_refine<TR_BM><<<(unsigned)(d.M / TR_BM), 256, tr_smem(TR_BM), st>>>(d);
     count_launch();
     return PIGP_OK;
+}
+
+// 64-row slabs halve the re-streaming of the 128 x 128 operands once the panel covers the GPU; short panels (the
+// latency-bound regime of small N and of many ranks) keep 32-row slabs: twice the CTAs, half the work per CTA
+static int launch_trsm_refine(const GemmDesc& d, cudaStream_t st) {
+    return d.M >= 148 * 64 ? launch_trsm_refine_t<64>(d, st) : launch_trsm_refine_t<32>(d, st);
 }
 
 static int g_gemm_bn = 0;  // 0: read PIGP_GEMM_BN once (kernel tuning); 128 or 64
@@ -1117,8 +1128,10 @@ int preload_dense() {
     PIGP_CUDA(cudaFuncSetAttribute(k_gemm_s<64, 64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (64 + 64) * LDS_K * (int)sizeof(double)));
     PIGP_PRELOAD((k_gemm_s<32, 128, 3>));
     PIGP_PRELOAD((k_gemm_s<64, 64, 3>));
-    PIGP_CUDA(cudaFuncSetAttribute(k_trsm_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
-    PIGP_PRELOAD(k_trsm_refine);
+    PIGP_CUDA(cudaFuncSetAttribute(k_trsm_refine<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem(32)));
+    PIGP_CUDA(cudaFuncSetAttribute(k_trsm_refine<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem(64)));
+    PIGP_PRELOAD(k_trsm_refine<32>);
+    PIGP_PRELOAD(k_trsm_refine<64>);
     PIGP_TRY((gemm_attrs<128, 4>()));
     PIGP_TRY((gemm_attrs<64, 3>()));
     PIGP_CUDA(cudaFuncSetAttribute(k_potf2, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM));

@@ -820,8 +820,12 @@ static int dsolver_enqueue(pigp_dsolver* s, const double* theta_dev, const doubl
     const pigp_plan* p = s->plan;
     const int64_t ld = s->ld;
     Ctx c = make_ctx(s, st);
-    c.sb = g_side_stream ? s->sb : st;  // serial mode (per-kernel timing): everything on the chain stream
-    c.sc = g_side_stream ? s->sc : st;
+    // serial mode: everything on the chain stream -- for the per-kernel timing pass, and for three or more ranks that share
+    // one device (tests): the emulation would otherwise keep more streams with spinning waits alive than the device has
+    // independent hardware queues, and a producer queued behind another rank's wait would dead-lock until the time-out
+    const bool serial = !g_side_stream || (s->shared_device && s->world >= 3);
+    c.sb = serial ? st : s->sb;
+    c.sc = serial ? st : s->sc;
     c.grad = grad_dev != nullptr;
     int32_t* info = s->info;
     PIGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
@@ -847,7 +851,7 @@ static int dsolver_enqueue(pigp_dsolver* s, const double* theta_dev, const doubl
         count_launch();
     }
     PIGP_CUDA(cudaGetLastError());
-    if (lookahead_width() > 0 && g_side_stream && s->T > lookahead_width()) PIGP_TRY(chol_lookahead(c, lookahead_width()));
+    if (lookahead_width() > 0 && c.sb != st && s->T > lookahead_width()) PIGP_TRY(chol_lookahead(c, lookahead_width()));
     else PIGP_TRY(rec(c, 0, s->T));
     if (c.npeers > 0) {
         // the diagonal of every L_kk (log-det) travels with the DIAG flags; a GEMM only waits for the flags it consumes

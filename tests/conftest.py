@@ -6,6 +6,9 @@ import pytest
 # tests/test_gpu_dist.py runs several ranks (3 streams each, with spinning flag waits) inside one process: every stream
 # needs its own hardware queue or a wait in one stream stalls an unrelated one (the default is 8 queues per process)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# a dead-lock of that single-GPU emulation must fail a test in seconds, not after the production time-outs (10 s / 300 s)
+os.environ.setdefault("PIGP_WAIT_TIMEOUT_S", "6")
+os.environ.setdefault("PIGP_BARRIER_TIMEOUT_S", "20")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
