@@ -253,6 +253,7 @@ struct pigp_dsolver {
     bool shared_device = false;  // a peer rank lives on this device (tests): flag waits stay in their own 1-CTA kernels,
                                  // because a grid of spinning CTAs could starve the producer it is waiting for
     u64 epoch = 0;
+    bool y_lazy = false;  // Y is a separate allocation made on the first gradient request (world == 1)
     bool broken = false;  // an enqueue failed part-way through a call: the solver must be reset (or destroyed)
     // private (not shared)
     AsmTile* d_tiles = nullptr;
@@ -610,6 +611,7 @@ extern "C" {
 
 void pigp_dsolver_destroy(pigp_dsolver* s) {
     if (!s) return;
+    if (s->y_lazy) cudaFree(s->Y);
     cudaFree(s->slab); cudaFree(s->d_tiles); cudaFree(s->partials); cudaFree(s->gpart); cudaFree(s->out2); cudaFree(s->v);
     cudaFree(s->alpha); cudaFree(s->info); cudaFree(s->err); cudaFree(s->sig_counter); cudaFree(s->d_theta); cudaFree(s->d_y); cudaFree(s->d_res);
     if (s->h_res) cudaFreeHost(s->h_res);
@@ -643,7 +645,10 @@ int pigp_dsolver_create(pigp_plan* plan, int rank, int world, pigp_dsolver** out
     s->gy = s->first_own(s->T);
     s->n_flags = s->T + s->T * world + 3 * world;
     const size_t l_bytes = sizeof(double) * (size_t)(s->T + world) * TILE * s->ld;
-    const size_t y_bytes = sizeof(double) * (size_t)s->npad * s->ld;
+    // Y = L^-T is needed by the gradient only.  A single-rank solver (the handle behind pigp_solver: NLL-only and
+    // posterior users) allocates it on the first gradient request; sharded solvers keep it inside the peer-visible slab.
+    s->y_lazy = (world == 1);
+    const size_t y_bytes = s->y_lazy ? 0 : sizeof(double) * (size_t)s->npad * s->ld;
     const size_t i_bytes = sizeof(double) * (size_t)s->T * TILE * TILE;
     const size_t g_bytes = sizeof(double) * (size_t)world * MAX_THETA;
     const size_t f_bytes = (sizeof(u64) * (size_t)s->n_flags + 255) / 256 * 256;
@@ -656,7 +661,7 @@ int pigp_dsolver_create(pigp_plan* plan, int rank, int world, pigp_dsolver** out
     if (rc == PIGP_OK) {
         char* p = s->slab;
         s->L = reinterpret_cast<double*>(p); p += l_bytes;
-        s->Y = reinterpret_cast<double*>(p); p += y_bytes;
+        s->Y = s->y_lazy ? nullptr : reinterpret_cast<double*>(p); p += y_bytes;
         s->invd = reinterpret_cast<double*>(p); p += i_bytes;
         s->gslots = reinterpret_cast<double*>(p); p += (g_bytes + 255) / 256 * 256;
         s->flags = reinterpret_cast<u64*>(p);
@@ -833,6 +838,7 @@ static int dsolver_enqueue(pigp_dsolver* s, const double* theta_dev, const doubl
     PIGP_TRY(signal(c, s->f_bar(s->rank)));
     PIGP_TRY(wait_all(c, s->f_bar(0), st, barrier_timeout_ns()));
     const int first = s->first_own(0), cnt = s->count_own(0, s->T);
+    if (c.grad && !s->Y) PIGP_CUDA(cudaMalloc(&s->Y, sizeof(double) * (size_t)s->npad * s->ld));
     if (c.grad) {
         PIGP_CUDA(cudaEventRecord(s->ev_bar, st));
         PIGP_CUDA(cudaStreamWaitEvent(c.sb, s->ev_bar, 0));
@@ -938,6 +944,11 @@ int pigp_dsolver_reset(pigp_dsolver* s) {
     PIGP_CUDA(cudaStreamSynchronize(s->sc));
     PIGP_CUDA(cudaMemset(s->err, 0, sizeof(int)));
     PIGP_CUDA(cudaMemset(s->sig_counter, 0, 2 * sizeof(unsigned int)));
+    // the ranks' call counters may have drifted apart (a rank that never made the failed call): everybody restarts at
+    // epoch 0 with clean flags.  The host-side barrier AFTER the resets keeps a fast rank's new flags from being erased.
+    PIGP_CUDA(cudaMemset(s->flags, 0, sizeof(u64) * (size_t)s->n_flags));
+    PIGP_CUDA(cudaMemset(s->gslots, 0, sizeof(double) * (size_t)s->world * MAX_THETA));
+    s->epoch = 0;
     s->broken = false;
     return PIGP_OK;
 }

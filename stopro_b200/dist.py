@@ -132,6 +132,10 @@ class DistSolver:
                                                          C.addressof(info)))
         return nll.value, (grad if want_grad else None), info.value
 
+    def reset(self):
+        """Re-arm after a failed evaluation (a lost or late peer): call on every rank, then barrier on the host."""
+        _lib.check(_lib.lib().pigp_dsolver_reset(self.handle))
+
     def close(self):
         if getattr(self, "handle", None):
             _lib.lib().pigp_dsolver_destroy(self.handle)

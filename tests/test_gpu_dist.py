@@ -130,3 +130,45 @@ def test_lookahead_panel_schedule_matches_recursion(cuda_device, world, width):
         assert abs(nll - nll0) <= 1e-11 * abs(nll0)
         assert relerr(grad, grad0) <= 1e-9
     gp.close()
+
+
+def test_lost_peer_times_out_and_reset_recovers(cuda_device):
+    """a rank that never shows up must not hang a GPU.  Rank 0 evaluates alone: its opening barrier runs into
+    the (test-shortened) time-out, the host call reports it, results are NaN; after pigp_dsolver_reset on both ranks the
+    pair evaluates correctly."""
+    import time
+
+    from stopro_b200 import _lib
+
+    cfg = dict(synthetic.poiseuille(kernel_form="product"), eps=1e-2)
+    gp = synthetic.make_model(cfg)
+    ref = oracle_for(cfg)
+    r, y, eps = cfg["r_train"], cfg["delta_y"], cfg["eps"]
+    gp.set_constants(r, y, eps, only_training=True)
+    plan = gp._training_plan(r)
+    solvers = [DistSolver(plan, k, 2) for k in range(2)]
+    slabs = [s.slab()[0] for s in solvers]
+    for s in solvers:
+        s.connect_pointers(slabs)
+    t0 = time.perf_counter()
+    with pytest.raises(_lib.PigpError, match="timed out"):
+        solvers[0].nll_grad_host(cfg["theta0"], y, eps)
+    assert time.perf_counter() - t0 < 90.0
+    for s in solvers:
+        s.reset()
+    out = [None, None]
+
+    def work(k):
+        out[k] = solvers[k].nll_grad_host(cfg["theta0"], y, eps)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    nll_ref = ref.trainingFunction_all(cfg["theta0"], r, y, eps)
+    for nll, grad, info in out:
+        assert info == 0 and abs(nll - nll_ref) <= F_TOL * abs(nll_ref)
+    for s in solvers:
+        s.close()
+    gp.close()

@@ -85,3 +85,70 @@ def test_batched_and_diagonal_only_posterior(cuda_device):
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), np.diag(gp.testK_all(thetas[0], cfg["r_test"])))
     gp.close()
+
+
+def test_block_with_four_hyperparameter_groups(cuda_device):
+    """A block may draw on every hyper-parameter group of the model (PIGP_MAX_GROUPS = 4): K and the trace gradient of a
+    hand-made 3-D block  sum_g c_g D_g k_g  equal the sum of the four single-group blocks (the old evaluator
+    silently truncated a block to three groups)."""
+    import ctypes as C
+
+    import torch
+
+    from stopro_b200 import _lib, operators
+
+    lib = _lib.lib()
+    rng = np.random.default_rng(5)
+    n, dim, ng = 200, 3, 4
+    pts = np.ascontiguousarray(rng.random((n, dim)))
+    sec = np.array([0, n], dtype=np.int64)
+    orders = [(0, 0, 0), (2, 0, 0), (1, 1, 0), (0, 2, 2)]          # one monomial per group, mixed parities
+    coefs = [1.0, -0.7, 0.4, 0.25]
+
+    def make_plan(terms):
+        table = (_lib.BlockDesc * 1)()
+        table[0].n_terms = len(terms)
+        for k, (g, c, o) in enumerate(terms):
+            table[0].terms[k].group, table[0].terms[k].coef = g, c
+            for d in range(3):
+                table[0].terms[k].order[d] = o[d]
+        d = _lib.PlanDesc()
+        d.dim, d.product_form, d.n_groups, d.symmetric, d.n_row_blocks, d.n_col_blocks = dim, 1, ng, 1, 1, 1
+        d.sec_row = sec.ctypes.data_as(C.POINTER(C.c_int64))
+        d.sec_col = d.sec_row
+        d.pts_row_host = pts.ctypes.data_as(C.POINTER(C.c_double))
+        d.pts_col_host = d.pts_row_host
+        d.table = table
+        d.noise_lo_block = d.noise_hi_block = -1
+        h = C.c_void_p()
+        _lib.check(lib.pigp_plan_create(C.byref(d), C.byref(h)))
+        return h, table
+
+    theta = rng.normal(0.0, 0.3, ng * (1 + dim))
+    th_dev = torch.as_tensor(theta, device=cuda_device)
+
+    def assemble(h):
+        K = torch.empty(n, n, dtype=torch.float64, device=cuda_device)
+        _lib.check(lib.pigp_assemble(h, th_dev.data_ptr(), 0.0, 0, K.data_ptr(), n, _lib.LAYOUT_FULL, None))
+        torch.cuda.synchronize()
+        return K.cpu().numpy()
+
+    h_all, keep = make_plan([(g, coefs[g], orders[g]) for g in range(ng)])
+    K_all = assemble(h_all)
+    K_sum = np.zeros((n, n))
+    for g in range(ng):
+        h_g, keep_g = make_plan([(g, coefs[g], orders[g])])
+        K_sum += assemble(h_g)
+        lib.pigp_plan_destroy(h_g)
+    assert np.max(np.abs(K_all - K_sum)) <= 1e-13 * np.max(np.abs(K_sum))
+    # every group's gamma really is its own: scaling gamma_3 scales only the fourth monomial's share
+    theta2 = theta.copy()
+    theta2[3 * (1 + dim)] += np.log(2.0)
+    th_dev.copy_(torch.as_tensor(theta2))
+    h_3, keep_3 = make_plan([(3, coefs[3], orders[3])])
+    th_dev.copy_(torch.as_tensor(theta))
+    K_3 = assemble(h_3)
+    th_dev.copy_(torch.as_tensor(theta2))
+    assert np.max(np.abs(assemble(h_all) - (K_all + K_3))) <= 1e-13 * np.max(np.abs(K_all))
+    lib.pigp_plan_destroy(h_3)
+    lib.pigp_plan_destroy(h_all)

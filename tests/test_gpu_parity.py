@@ -51,18 +51,21 @@ def _gov_test(n_test):
 STRICT = {"sin1d_naive", "sin1d_laplacian", "drag3d", "poiseuille_additive_eps1e-2", "poiseuille_product_eps1e-2",
           "sinusoidal_eps1e-2"}
 U = 2.0 ** -52
+COND_FRAC = 0.05  # of the first-order forward-error bound cond(K) * u (the rule of tests/test_reference_pin.py)
 
 
 def solve_tol(ref, cfg, th, name):
     """1e-8 where the conditioning allows it.  Two correct FP64 evaluations of K differ by ~u per entry, and a
     solve against K amplifies that by up to cond(K): with eps = 1e-6 the schema-faithful 2-D Stokes instances have
     cond(K) ~ 1e9, where no pair of independent FP64 implementations can agree to 1e-8.
-    Those cases are held to cond(K) * u instead; the STRICT cases must be well conditioned enough for 1e-8."""
+    Those cases are held to 5 % of cond(K) * u instead (the reference-pinned fixtures of tests/test_reference_pin.py, with
+    their long-double truth, are the authoritative gate for them); the STRICT cases must be well conditioned enough for
+    1e-8."""
     cond = np.linalg.cond(ref.training_sigma(th, cfg["r_train"], cfg["eps"]))
     if name in STRICT:
         assert cond * U < F_TOL, f"{name}: cond={cond:.2e} is too large for a strict case"
         return F_TOL
-    return max(F_TOL, cond * U)
+    return max(F_TOL, COND_FRAC * cond * U)
 
 
 def relerr(a, b):
