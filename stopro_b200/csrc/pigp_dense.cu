@@ -408,14 +408,22 @@ static int launch_gemm_small(const GemmDesc& d, cudaStream_t st) {
 constexpr int TR_SLD = 128 + 8, TR_STAGES = 3;
 __host__ __device__ constexpr int tr_smem(int bm) { return (2 * bm * TR_SLD + TR_STAGES * 128 * LDS_K) * (int)sizeof(double); }
 
+// Warp layout of a TR_BM x 128 slab: TR_WM warps along the rows (8 * TR_MI rows each), 8 / TR_WM along the columns
+// (8 * TR_NI columns each).  TR_BM = 8 / 16 keep the per-CTA DMMA chain short for the latency-bound panels of small N.
+template <int TR_BM> struct TrShape {
+    static constexpr int WM = TR_BM >= 16 ? 2 : 1, WN = 8 / WM;
+    static constexpr int MI = TR_BM / (8 * WM), NI = 16 / WN;
+};
+
 template <int TR_BM>
-__device__ __forceinline__ void trsm_stage(const double* S, const double* Bg, int64_t ldb, double* sB, double (&acc)[TR_BM / 16][4][2],
-                                           int tid, int wm, int wn, int gid, int tig) {
-    constexpr int TR_MI = TR_BM / 16;
+__device__ __forceinline__ void trsm_stage(const double* S, const double* Bg, int64_t ldb, double* sB,
+                                           double (&acc)[TrShape<TR_BM>::MI][TrShape<TR_BM>::NI][2], int tid, int wm, int wn, int gid, int tig) {
+    using Sh = TrShape<TR_BM>;
+    constexpr int TR_MI = Sh::MI, TR_NI = Sh::NI;
 #pragma unroll
     for (int i = 0; i < TR_MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < TR_NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     constexpr int NK = 128 / BK, OPB = 128 * LDS_K;
 #pragma unroll
     for (int s = 0; s < TR_STAGES - 1; ++s) {
@@ -433,19 +441,19 @@ __device__ __forceinline__ void trsm_stage(const double* S, const double* Bg, in
         const double* b = sB + (it % TR_STAGES) * OPB;
 #pragma unroll
         for (int k8 = 0; k8 < BK; k8 += 8) {
-            double2 af[TR_MI], bf[4];
+            double2 af[TR_MI], bf[TR_NI];
 #pragma unroll
             for (int mi = 0; mi < TR_MI; ++mi)
-                af[mi] = *reinterpret_cast<const double2*>(S + (wm * (TR_BM / 2) + 8 * mi + gid) * TR_SLD + it * BK + k8 + 2 * tig);
-            load_frags<true, 4, 128>(bf, b, wn * 32, k8, gid, tig);
-#pragma unroll
-            for (int mi = 0; mi < TR_MI; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi].x, bf[ni].x);
+                af[mi] = *reinterpret_cast<const double2*>(S + (wm * 8 * TR_MI + 8 * mi + gid) * TR_SLD + it * BK + k8 + 2 * tig);
+            load_frags<true, TR_NI, 128>(bf, b, wn * 8 * TR_NI, k8, gid, tig);
 #pragma unroll
             for (int mi = 0; mi < TR_MI; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi].y, bf[ni].y);
+                for (int ni = 0; ni < TR_NI; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi].x, bf[ni].x);
+#pragma unroll
+            for (int mi = 0; mi < TR_MI; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < TR_NI; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi].y, bf[ni].y);
         }
     }
     cp_async_wait<0>();
@@ -454,14 +462,15 @@ __device__ __forceinline__ void trsm_stage(const double* S, const double* Bg, in
 
 template <int TR_BM>
 __global__ void __launch_bounds__(256) k_trsm_refine(GemmDesc g) {
-    constexpr int TR_MI = TR_BM / 16;
+    using Sh = TrShape<TR_BM>;
+    constexpr int TR_MI = Sh::MI, TR_NI = Sh::NI;
     extern __shared__ __align__(16) double smem[];
     double* S0 = smem;                       // A, later the residual R
     double* S1 = S0 + TR_BM * TR_SLD;        // X0
     double* sB = S1 + TR_BM * TR_SLD;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
-    const int wm = warp & 1, wn = warp >> 1;
+    const int wm = warp % Sh::WM, wn = warp / Sh::WM;
     constexpr int SUB = BM / TR_BM;
     const int tm = blockIdx.x;
     const int64_t m0 = (int64_t)(tm / SUB) * g.m_ts * BM + (tm % SUB) * TR_BM;
@@ -474,30 +483,26 @@ __global__ void __launch_bounds__(256) k_trsm_refine(GemmDesc g) {
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    double acc[TR_MI][4][2];
+    double acc[TR_MI][TR_NI][2];
     // X0 = A W^T -> S1
     trsm_stage<TR_BM>(S0, g.B, g.ldb, sB, acc, tid, wm, wn, gid, tig);
 #pragma unroll
     for (int mi = 0; mi < TR_MI; ++mi)
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            double* row = S1 + (wm * (TR_BM / 2) + 8 * mi + gid) * TR_SLD + wn * 32 + 16 * q + 2 * tig;
-            *reinterpret_cast<double2*>(row) = make_double2(acc[mi][2 * q][0], acc[mi][2 * q][1]);
-            *reinterpret_cast<double2*>(row + 8) = make_double2(acc[mi][2 * q + 1][0], acc[mi][2 * q + 1][1]);
-        }
+        for (int ni = 0; ni < TR_NI; ++ni)
+            *reinterpret_cast<double2*>(S1 + (wm * 8 * TR_MI + 8 * mi + gid) * TR_SLD + wn * 8 * TR_NI + 8 * ni + 2 * tig) =
+                make_double2(acc[mi][ni][0], acc[mi][ni][1]);
     __syncthreads();
     // R = A - X0 Lkk^T -> S0
     trsm_stage<TR_BM>(S1, g.Lkk, g.ldl, sB, acc, tid, wm, wn, gid, tig);
 #pragma unroll
     for (int mi = 0; mi < TR_MI; ++mi)
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            double* row = S0 + (wm * (TR_BM / 2) + 8 * mi + gid) * TR_SLD + wn * 32 + 16 * q + 2 * tig;
-            double2 a0 = *reinterpret_cast<double2*>(row), a1 = *reinterpret_cast<double2*>(row + 8);
-            a0.x -= acc[mi][2 * q][0]; a0.y -= acc[mi][2 * q][1];
-            a1.x -= acc[mi][2 * q + 1][0]; a1.y -= acc[mi][2 * q + 1][1];
-            *reinterpret_cast<double2*>(row) = a0;
-            *reinterpret_cast<double2*>(row + 8) = a1;
+        for (int ni = 0; ni < TR_NI; ++ni) {
+            double2* e = reinterpret_cast<double2*>(S0 + (wm * 8 * TR_MI + 8 * mi + gid) * TR_SLD + wn * 8 * TR_NI + 8 * ni + 2 * tig);
+            double2 a0 = *e;
+            a0.x -= acc[mi][ni][0]; a0.y -= acc[mi][ni][1];
+            *e = a0;
         }
     __syncthreads();
     // X = X0 + R W^T -> global (in place)
@@ -505,13 +510,10 @@ __global__ void __launch_bounds__(256) k_trsm_refine(GemmDesc g) {
 #pragma unroll
     for (int mi = 0; mi < TR_MI; ++mi)
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int lr = wm * (TR_BM / 2) + 8 * mi + gid, lc = wn * 32 + 16 * q + 2 * tig;
+        for (int ni = 0; ni < TR_NI; ++ni) {
+            const int lr = wm * 8 * TR_MI + 8 * mi + gid, lc = wn * 8 * TR_NI + 8 * ni + 2 * tig;
             const double2 x0 = *reinterpret_cast<const double2*>(S1 + lr * TR_SLD + lc);
-            const double2 x1 = *reinterpret_cast<const double2*>(S1 + lr * TR_SLD + lc + 8);
-            double* out = g.C + (m0 + lr) * g.ldc + lc;
-            *reinterpret_cast<double2*>(out) = make_double2(x0.x + acc[mi][2 * q][0], x0.y + acc[mi][2 * q][1]);
-            *reinterpret_cast<double2*>(out + 8) = make_double2(x1.x + acc[mi][2 * q + 1][0], x1.y + acc[mi][2 * q + 1][1]);
+            *reinterpret_cast<double2*>(g.C + (m0 + lr) * g.ldc + lc) = make_double2(x0.x + acc[mi][ni][0], x0.y + acc[mi][ni][1]);
         }
 }
 
@@ -535,10 +537,14 @@ static int launch_trsm_refine_t(const GemmDesc& d, cudaStream_t st) {
     return PIGP_OK;
 }
 
-// 64-row slabs halve the re-streaming of the 128 x 128 operands once the panel covers the GPU; short panels (the
-// latency-bound regime of small N and of many ranks) keep 32-row slabs: twice the CTAs, half the work per CTA
+// 64-row slabs halve the re-streaming of the 128 x 128 operands once the panel covers the GPU.  Shorter panels are latency
+// bound -- the three products of a slab run back to back on one SM's FP64 tensor pipe, 3 x 2 x rows x 128 x 128 flops at
+// ~126 flop/clk -- so the slab height shrinks with the panel until the CTAs no longer cover the 148 SMs.
 static int launch_trsm_refine(const GemmDesc& d, cudaStream_t st) {
-    return d.M >= 148 * 64 ? launch_trsm_refine_t<64>(d, st) : launch_trsm_refine_t<32>(d, st);
+    if (d.M >= 148 * 64) return launch_trsm_refine_t<64>(d, st);
+    if (d.M > 148 * 16) return launch_trsm_refine_t<32>(d, st);
+    if (d.M > 148 * 8) return launch_trsm_refine_t<16>(d, st);
+    return launch_trsm_refine_t<8>(d, st);
 }
 
 static int g_gemm_bn = 0;  // 0: read PIGP_GEMM_BN once (kernel tuning); 128 or 64
@@ -613,6 +619,11 @@ int launch_gemm(const GemmDesc& g_in, cudaStream_t st) {
             return PIGP_OK;
         }
         const int64_t tiles = (int64_t)(g.M / BM) * (g.N / 64) / (g.lower_only ? 2 : 1);
+        if (!g.force_bn128 && tiles < 74) {  // under half a wave of 64 x 64 tiles: halve the per-CTA DMMA chain instead
+            PIGP_TRY((launch_gemm_small<32, 64, 3>(g, st)));
+            PIGP_CUDA(cudaGetLastError());
+            return PIGP_OK;
+        }
         if (!g.force_bn128 && tiles < 2 * 148) {
             PIGP_TRY((launch_gemm_small<64, 64, 3>(g, st)));
             PIGP_CUDA(cudaGetLastError());
@@ -650,7 +661,7 @@ constexpr int PT = 128;
 constexpr int PLD = PT + 4;   // 132 = 4 mod 16: conflict-free DMMA fragment loads in both orientations
 constexpr int SLD = 36;       // 32 x 32 scratch blocks, same residue
 constexpr int N_SCRATCH = 6;  // inv(L_kk) x 4, two temporaries
-constexpr int POTF2_SMEM = (PT * PLD + N_SCRATCH * 32 * SLD + 32 + 128) * (int)sizeof(double);
+constexpr int POTF2_SMEM = (PT * PLD + N_SCRATCH * 32 * SLD + 2 * 32 * 4) * (int)sizeof(double);
 
 // C(8 x 32 strip) = (accumulate ? C : 0) + alpha * sum_k A(row, k) * Bop(col, k);  Bop(col,k) = B_KN ? B[k][col] : B[col][k].
 // Pointers are pre-offset to the strip / operand origin.  n_tiles (1..4) of the four 8 x 8 column tiles are stored.
@@ -699,58 +710,109 @@ __device__ __forceinline__ void strip_mma(double* C, int ldc, const double* A, i
 __device__ long long* g_potf2_dbg = nullptr;  // optional phase stamps (tools/potf2_bench.py)
 #define POTF2_STAMP(i) do { if (g_potf2_dbg && threadIdx.x == 0) g_potf2_dbg[i] = clock64(); } while (0)
 
+// 1 / sqrt(d) for the pivots: MUFU seed (~20 bits, from the high word) and one third-order correction,
+// y (1 + e/2 + 3 e^2/8) with e = 1 - d y^2 -- ~1 ulp, 5 dependent FP64 operations, branch-free (two of them interleave).
+// d < 0 or NaN -> NaN, d = 0 -> NaN as well (inf * 0): a failed factorisation is NaN from that column on.
+__device__ __forceinline__ double rsqrt_pivot(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double e = fma(-(d * y), y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    return fma(y * e, p, y);
+}
+
 // Warp-level Cholesky + inverse of the 32 x 32 block at D (shared memory, row stride ld).
-// Factor: lane i owns row i in registers; per column one broadcast of the pivot, one rsqrt, and the rank-1 update with
-// the column exchanged by shuffles.  Every lane also tracks its own future pivot S[i][i] locally (piv -= L[i][j]^2), so
-// the pivot -> rsqrt -> scale -> pivot chain never waits for the column exchange.
-// Inverse: L goes back to shared memory, then lane c solves column c of W = inv(L) right-looking
-// (w_i = r_i / L_ii; r_m -= L[m][i] w_i), the factor's entries coming from broadcast shared loads.
+// Lane i owns row i of the block in registers and column i of W = inv(L).  The 32 columns are eliminated in 16 pairs:
+// for the 2 x 2 pivot block [d0 b; b d1] the two reciprocal roots rsqrt(d0) and rsqrt(d0 d1 - b^2) are independent, so
+// the pivot -> rsqrt -> scale -> pivot dependency chain has 16 links instead of 32.  Per pair every lane publishes
+// (L[i][j], L[i][j+1], its own future pivot S[i][i], S[i][j+2]) in shared memory -- one exchange -- from which all lanes
+// rebuild the next pivot block redundantly; the rank-2 update of the rows and the right-looking solve of W's columns
+// (w_j = r_j / L_jj; r_m -= L[m][j] w_j) share the broadcast loads of the two new columns and fill the chain's bubbles.
 // L overwrites the lower triangle of D (zeros above); W goes to Winv (row stride SLD, zeros above).
-__device__ __forceinline__ void warp_potrf32(double* D, int ld, double* Winv, double* rdiag_sm, int32_t* info, int base, int lane) {
-    // rdiag_sm: 32 doubles for 1 / L_ii, followed by a double-buffered exchange area of 2 x 32 double2 (column, pivot)
-    double2* xch = reinterpret_cast<double2*>(rdiag_sm + 32);
-    double a[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? D[lane * ld + c] : 0.0;
-    double piv = D[lane * ld + lane];
-    double my_rdiag = 0.0;  // 1 / L[lane][lane]
-    xch[lane] = make_double2(0.0, piv);
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        // one exchange per column through shared memory (a warp shuffle of a double costs two SHFL plus a convergence
-        // barrier inside this warp-specialised branch): buffer j & 1 holds (L[i][j-1], pivot candidate S[i][i]) of lane i
-        const double d = xch[(j & 1) * 32 + j].y;
-        if (lane == 0 && !(d > 0.0) && info) atomicCAS(info, 0, base + j + 1);
-        const double rinv = rsqrt(d);  // NaN for d < 0, like the reference's jnp.linalg.cholesky
-        const double aj = (lane > j) ? a[j] * rinv : ((lane == j) ? d * rinv : 0.0);
-        a[j] = aj;
-        if (lane == j) my_rdiag = rinv;
-        piv = fma(-aj, aj, piv);
-        double2* nxt = xch + ((j + 1) & 1) * 32;
-        nxt[lane] = make_double2(aj, piv);
+struct __align__(16) PairXch { double l0, l1, piv, sub; };
+
+// (template recursion instead of #pragma unroll: the rows and columns must stay in registers, and the unroller gives up on
+// the long inner loops of the first pairs, which would put both arrays into local memory)
+template <int K>
+__device__ __forceinline__ void pair_update(double (&a)[32], double (&r)[32], const PairXch* nxt, double l0, double l1,
+                                            double w0, double w1) {
+    if constexpr (K < 32) {
+        const double2 c = *reinterpret_cast<const double2*>(&nxt[K].l0);  // (L[K][j], L[K][j+1]): broadcast load
+        a[K] = fma(-l1, c.y, fma(-l0, c.x, a[K]));
+        r[K] = fma(-c.y, w1, fma(-c.x, w0, r[K]));
+        pair_update<K + 1>(a, r, nxt, l0, l1, w0, w1);
+    }
+}
+
+template <int J>
+__device__ __forceinline__ void pair_step(double (&a)[32], double (&r)[32], double& piv, double d0, double d1, double b,
+                                          PairXch* xch, double* D, int ld, double* Winv, int32_t* info, int base, int lane) {
+    if constexpr (J < 32) {
+        const double b2 = b * b;
+        const double det = fma(d0, d1, -b2) - fma(b, b, -b2);  // d0 d1 - b^2 with the rounding of b^2 compensated
+        if (lane == 0 && info) {
+            if (!(d0 > 0.0)) atomicCAS(info, 0, base + J + 1);
+            else if (!(det > 0.0)) atomicCAS(info, 0, base + J + 2);
+        }
+        const double r0 = rsqrt_pivot(d0), rdet = rsqrt_pivot(det);
+        const double l00 = d0 * r0;            // sqrt(d0)
+        const double l10 = b * r0;
+        const double l11 = (det * rdet) * r0;  // sqrt(d1 - b^2 / d0)
+        const double r1 = rdet * l00;          // 1 / l11
+        double l0, l1;
+        if (lane > J + 1) {
+            l0 = a[J] * r0;
+            l1 = fma(-l0, l10, a[J + 1]) * r1;
+        } else {
+            l0 = (lane == J) ? l00 : ((lane == J + 1) ? l10 : 0.0);
+            l1 = (lane == J + 1) ? l11 : 0.0;
+        }
+        piv = fma(-l1, l1, fma(-l0, l0, piv));
+        PairXch* nxt = xch + (((J >> 1) + 1) & 1) * 32;
+        {
+            PairXch e;
+            e.l0 = l0; e.l1 = l1; e.piv = piv;
+            if constexpr (J + 2 < 32) e.sub = a[J + 2]; else e.sub = 0.0;
+            nxt[lane] = e;
+        }
+        // columns J, J + 1 of L and rows J, J + 1 of W are final: back to shared memory at once (frees their registers)
+        *reinterpret_cast<double2*>(D + lane * ld + J) = make_double2(l0, l1);
+        const double w0 = r[J] * r0;
+        const double w1 = fma(-l10, w0, r[J + 1]) * r1;
+        Winv[J * SLD + lane] = w0;
+        Winv[(J + 1) * SLD + lane] = w1;
         __syncwarp();
-#pragma unroll
-        for (int k = j + 1; k < 32; ++k) a[k] = fma(-aj, nxt[k].x, a[k]);  // L[k][j]: broadcast load
+        double nd0 = 0.0, nd1 = 0.0, nb = 0.0;
+        if constexpr (J + 3 < 32) {
+            const PairXch p2 = nxt[J + 2], p3 = nxt[J + 3];
+            nd0 = p2.piv;
+            nd1 = p3.piv;
+            nb = fma(-p3.l1, p2.l1, fma(-p3.l0, p2.l0, p3.sub));
+        }
+        pair_update<J + 2>(a, r, nxt, l0, l1, w0, w1);
+        pair_step<J + 2>(a, r, piv, nd0, nd1, nb, xch, D, ld, Winv, info, base, lane);
     }
-    POTF2_STAMP(13);
+}
+
+__device__ __forceinline__ void warp_potrf32(double* D, int ld, double* Winv, double* xch_sm, int32_t* info, int base, int lane) {
+    PairXch* xch = reinterpret_cast<PairXch*>(xch_sm);  // 2 x 32 entries, double-buffered
+    double a[32], r[32];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) D[lane * ld + c] = (c <= lane) ? a[c] : 0.0;
-    rdiag_sm[lane] = my_rdiag;
+    for (int c = 0; c < 32; ++c) {
+        a[c] = (c <= lane) ? D[lane * ld + c] : 0.0;
+        r[c] = (c == lane) ? 1.0 : 0.0;
+    }
+    double piv = D[lane * ld + lane];
+    {
+        PairXch e;
+        e.l0 = 0.0; e.l1 = 0.0; e.piv = piv; e.sub = a[0];  // lane 1: S[1][0]
+        xch[lane] = e;
+    }
     __syncwarp();
-    double r[32];
-#pragma unroll
-    for (int m = 0; m < 32; ++m) r[m] = (m == lane) ? 1.0 : 0.0;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        const double w = r[i] * rdiag_sm[i];
-        r[i] = w;
-#pragma unroll
-        for (int m = i + 1; m < 32; ++m) r[m] = fma(-D[m * ld + i], w, r[m]);
-    }
+    pair_step<0>(a, r, piv, xch[0].piv, xch[1].piv, xch[1].sub, xch, D, ld, Winv, info, base, lane);
+    POTF2_STAMP(13);
+    __syncwarp();
     POTF2_STAMP(14);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) Winv[i * SLD + lane] = r[i];
 }
 
 // Factor the lower triangle of the 128 x 128 tile at A in place (the upper part of the tile is set to zero) and write
@@ -760,7 +822,7 @@ __device__ __forceinline__ void warp_potrf32(double* D, int ld, double* Winv, do
 __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double* invd, int32_t* info, int base, PeerTiles peers) {
     extern __shared__ __align__(16) double sm[];
     double* scratch = sm + PT * PLD;
-    double* rdiag = scratch + N_SCRATCH * 32 * SLD;  // 32 doubles
+    double* rdiag = scratch + N_SCRATCH * 32 * SLD;  // exchange area of warp_potrf32: 2 x 32 x 4 doubles
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     POTF2_STAMP(0);
     // tile -> shared memory (16-byte asynchronous copies, all in flight at once), then zero the strict upper triangle
@@ -1126,10 +1188,16 @@ int launch_gemv(const double* A, int64_t ld, int64_t m, int64_t n, const double*
 int preload_dense() {
     PIGP_CUDA(cudaFuncSetAttribute(k_gemm_s<32, 128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (32 + 128) * LDS_K * (int)sizeof(double)));
     PIGP_CUDA(cudaFuncSetAttribute(k_gemm_s<64, 64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (64 + 64) * LDS_K * (int)sizeof(double)));
+    PIGP_CUDA(cudaFuncSetAttribute(k_gemm_s<32, 64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (32 + 64) * LDS_K * (int)sizeof(double)));
     PIGP_PRELOAD((k_gemm_s<32, 128, 3>));
     PIGP_PRELOAD((k_gemm_s<64, 64, 3>));
+    PIGP_PRELOAD((k_gemm_s<32, 64, 3>));
+    PIGP_CUDA(cudaFuncSetAttribute(k_trsm_refine<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem(8)));
+    PIGP_CUDA(cudaFuncSetAttribute(k_trsm_refine<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem(16)));
     PIGP_CUDA(cudaFuncSetAttribute(k_trsm_refine<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem(32)));
     PIGP_CUDA(cudaFuncSetAttribute(k_trsm_refine<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem(64)));
+    PIGP_PRELOAD(k_trsm_refine<8>);
+    PIGP_PRELOAD(k_trsm_refine<16>);
     PIGP_PRELOAD(k_trsm_refine<32>);
     PIGP_PRELOAD(k_trsm_refine<64>);
     PIGP_TRY((gemm_attrs<128, 4>()));

@@ -515,10 +515,16 @@ int rec(const Ctx& c, int c0, int nt) {
 // panel p to the columns of panel p + 1 first (the chain waits only for that) and to the rest afterwards, concurrently
 // with the chain's work on panel p + 1.  The big trailing updates thereby leave the N/128-step dependency chain; the
 // L^-T products get the matching right-looking update V_p on the side stream.  Uses the existing kernels only.
-static int g_lookahead = -1;  // -1: read PIGP_LOOKAHEAD once; set by pigp_set_lookahead
-static int lookahead_width() {
-    if (g_lookahead < 0) { const char* e = getenv("PIGP_LOOKAHEAD"); g_lookahead = e ? std::max(0, atoi(e)) : 0; }
-    return g_lookahead;
+// Width: PIGP_LOOKAHEAD / pigp_set_lookahead(W >= 0) fix it (0 = plain recursion); unset (or a negative W) = automatic:
+// a single-rank NLL-only evaluation has no L^-T work on the side stream to fill the bubbles of the potf2 -> TRSM chain,
+// and the panel schedule measured 18 % / 13 % / 5 % faster there at N = 5018 / 10570 / 20000 (profiles/r02_lookahead.txt);
+// with the gradient requested, or sharded, the plain recursion is within 3 % and stays the default.
+static int g_lookahead = -2;  // -2: read PIGP_LOOKAHEAD once; -1: automatic; >= 0: fixed
+static int lookahead_width(const pigp_dsolver* s, bool grad) {
+    if (g_lookahead == -2) { const char* e = getenv("PIGP_LOOKAHEAD"); g_lookahead = e ? std::max(0, atoi(e)) : -1; }
+    if (g_lookahead >= 0) return g_lookahead;
+    if (grad || s->world != 1 || s->T < 12) return 0;
+    return s->T < 64 ? 2 : s->T < 128 ? 4 : 8;
 }
 
 static int ensure_lookahead(pigp_dsolver* s) {
@@ -713,7 +719,7 @@ int pigp_dsolver_create(pigp_plan* plan, int rank, int world, pigp_dsolver** out
 }
 
 int pigp_set_lookahead(int tiles) {
-    g_lookahead = tiles < 0 ? 0 : tiles;
+    g_lookahead = tiles < 0 ? -1 : tiles;
     return PIGP_OK;
 }
 
@@ -857,7 +863,8 @@ static int dsolver_enqueue(pigp_dsolver* s, const double* theta_dev, const doubl
         count_launch();
     }
     PIGP_CUDA(cudaGetLastError());
-    if (lookahead_width() > 0 && c.sb != st && s->T > lookahead_width()) PIGP_TRY(chol_lookahead(c, lookahead_width()));
+    const int law = lookahead_width(s, c.grad);
+    if (law > 0 && c.sb != st && s->T > law) PIGP_TRY(chol_lookahead(c, law));
     else PIGP_TRY(rec(c, 0, s->T));
     if (c.npeers > 0) {
         // the diagonal of every L_kk (log-det) travels with the DIAG flags; a GEMM only waits for the flags it consumes

@@ -124,11 +124,46 @@ def test_lookahead_panel_schedule_matches_recursion(cuda_device, world, width):
         _lib.check(_lib.lib().pigp_set_lookahead(width))
         out = run_ranks(gp, cfg, cfg["theta0"], world, repeats=2)
     finally:
-        _lib.check(_lib.lib().pigp_set_lookahead(0))
+        _lib.check(_lib.lib().pigp_set_lookahead(-1))
     for (nll, grad, info), (nll0, grad0, _) in zip(out, base):
         assert info == 0
         assert abs(nll - nll0) <= 1e-11 * abs(nll0)
         assert relerr(grad, grad0) <= 1e-9
+    gp.close()
+
+
+def test_automatic_panel_schedule_for_nll_only(cuda_device):
+    """Default (automatic) width: a single-GPU NLL-only evaluation of >= 12 tiles takes the panel schedule; the value must
+    agree with the plain recursion (width 0) and with the NLL half of the NLL+gradient call."""
+    import torch
+
+    from stopro_b200 import _lib
+
+    cfg = dict(synthetic.stokes2d_scaling(2000, n_test=8), eps=1.0)   # 16 tiles -> automatic width 2
+    gp = synthetic.make_model(cfg)
+    gp.set_constants(cfg["r_train"], cfg["delta_y"], cfg["eps"], only_training=True)
+    solver = gp._solver_for(cfg["r_train"])
+    dev = torch.device("cuda:0")
+    theta = torch.as_tensor(cfg["theta0"], device=dev)
+    y = torch.as_tensor(cfg["delta_y"], device=dev)
+    out = torch.zeros(1 + solver.plan.theta_len, dtype=torch.float64, device=dev)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    vals = {}
+    try:
+        for w in (0, -1):
+            _lib.check(_lib.lib().pigp_set_lookahead(w))
+            for _ in range(2):
+                solver.nll(theta.data_ptr(), y.data_ptr(), cfg["eps"], out.data_ptr(), info.data_ptr(), None)
+            torch.cuda.synchronize()
+            assert int(info.item()) == 0
+            vals[w] = float(out[0].item())
+    finally:
+        _lib.check(_lib.lib().pigp_set_lookahead(-1))
+    solver.nll_grad(theta.data_ptr(), y.data_ptr(), cfg["eps"], out.data_ptr(), out.data_ptr() + 8, info.data_ptr(), None)
+    torch.cuda.synchronize()
+    both = float(out[0].item())
+    assert abs(vals[-1] - vals[0]) <= 1e-11 * abs(vals[0])
+    assert abs(vals[-1] - both) <= 1e-11 * abs(both)
     gp.close()
 
 

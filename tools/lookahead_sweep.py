@@ -9,6 +9,7 @@ from stopro_b200 import _lib, synthetic
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 widths = [int(w) for w in (sys.argv[2] if len(sys.argv) > 2 else "0,4,8,16,32").split(",")]
+nll_only = len(sys.argv) > 3 and sys.argv[3] == "nll"
 cfg = synthetic.stokes2d_scaling(n, n_test=16)
 gp = synthetic.make_model(cfg)
 gp.set_constants(cfg["r_train"], cfg["delta_y"], cfg["eps"], only_training=True)
@@ -25,7 +26,10 @@ for w in widths:
     for it in range(4):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        solver.nll_grad(theta.data_ptr(), y.data_ptr(), cfg["eps"], out.data_ptr(), out.data_ptr() + 8, None, None)
+        if nll_only:
+            solver.nll(theta.data_ptr(), y.data_ptr(), cfg["eps"], out.data_ptr(), None, None)
+        else:
+            solver.nll_grad(theta.data_ptr(), y.data_ptr(), cfg["eps"], out.data_ptr(), out.data_ptr() + 8, None, None)
         e1.record()
         torch.cuda.synchronize()
         if it:
@@ -34,5 +38,5 @@ for w in widths:
     if ref is None:
         ref = res
     import numpy as np
-    print(f"N={n} lookahead={w:3d}: {best:9.3f} ms   nll={res[0]:.9f}   max rel diff vs W=0: "
+    print(f"N={n} {'NLL only' if nll_only else 'NLL+grad'} lookahead={w:3d}: {best:9.3f} ms   nll={res[0]:.9f}   max rel diff vs W=0: "
           f"{np.max(np.abs(res - ref) / np.maximum(np.abs(ref), 1e-300)):.2e}", flush=True)
