@@ -661,7 +661,7 @@ constexpr int PT = 128;
 constexpr int PLD = PT + 4;   // 132 = 4 mod 16: conflict-free DMMA fragment loads in both orientations
 constexpr int SLD = 36;       // 32 x 32 scratch blocks, same residue
 constexpr int N_SCRATCH = 6;  // inv(L_kk) x 4, two temporaries
-constexpr int POTF2_SMEM = (PT * PLD + N_SCRATCH * 32 * SLD + 2 * 32 * 4) * (int)sizeof(double);
+constexpr int POTF2_SMEM = (PT * PLD + N_SCRATCH * 32 * SLD + 2 * 32 * 4 + 32 + 16) * (int)sizeof(double);
 
 // C(8 x 32 strip) = (accumulate ? C : 0) + alpha * sum_k A(row, k) * Bop(col, k);  Bop(col,k) = B_KN ? B[k][col] : B[col][k].
 // Pointers are pre-offset to the strip / operand origin.  n_tiles (1..4) of the four 8 x 8 column tiles are stored.
@@ -721,52 +721,72 @@ __device__ __forceinline__ double rsqrt_pivot(double d) {
     return fma(y * e, p, y);
 }
 
-// Warp-level Cholesky + inverse of the 32 x 32 block at D (shared memory, row stride ld).
-// Lane i owns row i of the block in registers and column i of W = inv(L).  The 32 columns are eliminated in 16 pairs:
-// for the 2 x 2 pivot block [d0 b; b d1] the two reciprocal roots rsqrt(d0) and rsqrt(d0 d1 - b^2) are independent, so
-// the pivot -> rsqrt -> scale -> pivot dependency chain has 16 links instead of 32.  Per pair every lane publishes
+// Warp-level Cholesky of the 32 x 32 block at D (shared memory, row stride ld), and its inverse by a second warp.
+// Factor (warp_factor32): lane i owns row i of the block in registers.  The 32 columns are eliminated in 16 pairs: for
+// the 2 x 2 pivot block [d0 b; b d1] the two reciprocal roots rsqrt(d0) and rsqrt(d0 d1 - b^2) are independent, so the
+// pivot -> rsqrt -> scale -> pivot dependency chain has 16 links instead of 32.  Per pair every lane publishes
 // (L[i][j], L[i][j+1], its own future pivot S[i][i], S[i][j+2]) in shared memory -- one exchange -- from which all lanes
-// rebuild the next pivot block redundantly; the rank-2 update of the rows and the right-looking solve of W's columns
-// (w_j = r_j / L_jj; r_m -= L[m][j] w_j) share the broadcast loads of the two new columns and fill the chain's bubbles.
-// L overwrites the lower triangle of D (zeros above); W goes to Winv (row stride SLD, zeros above).
+// rebuild the next pivot block redundantly, ahead of the rank-2 update of the rows, so that the chain (~13 dependent FP64
+// operations of ~20 cycles) runs underneath the update.  L overwrites the lower triangle of D (zeros above).
+// Inverse (warp_inverse32): lane c solves column c of W = inv(L) right-looking (w_j = r_j / L_jj; r_m -= L[m][j] w_j),
+// two columns of L at a time as soon as the factoring warp has released them (one mbarrier per column pair), with
+// the factor's entries coming from broadcast loads.  W goes to Winv (row stride SLD, zeros above the diagonal).
 struct __align__(16) PairXch { double l0, l1, piv, sub; };
 
-// (template recursion instead of #pragma unroll: the rows and columns must stay in registers, and the unroller gives up on
-// the long inner loops of the first pairs, which would put both arrays into local memory)
+// Shared-memory mbarriers hand the finished column pairs from the factoring warp to the inverting warp: arrive (release)
+// does not block the producer, try_wait (acquire) orders the consumer's loads behind the producer's stores.
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("{\n .reg .b64 t;\n mbarrier.arrive.shared::cta.b64 t, [%0];\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+// Scalars of the 2 x 2 pivot block [d0 b; b d1]: 1 / l00, l10 and 1 / l11 of its Cholesky factor.  Branch-free (a
+// non-positive pivot is recorded in `fail`, 1-based column inside the block, first one wins; NaNs propagate).
+struct PairScal { double r0, l10, r1; };
+
+__device__ __forceinline__ PairScal pivot_block(double d0, double d1, double b, int col, int& fail) {
+    const double b2 = b * b;
+    const double det = fma(d0, d1, -b2) - fma(b, b, -b2);  // d0 d1 - b^2 with the rounding of b^2 compensated
+    fail = (fail == 0 && !(d0 > 0.0)) ? col + 1 : fail;
+    fail = (fail == 0 && !(det > 0.0)) ? col + 2 : fail;
+    const double r0 = rsqrt_pivot(d0), rdet = rsqrt_pivot(det);
+    PairScal sc;
+    sc.r0 = r0;
+    sc.l10 = b * r0;
+    sc.r1 = rdet * (d0 * r0);  // sqrt(d0 / det) = 1 / sqrt(d1 - b^2 / d0)
+    return sc;
+}
+
+// (template recursion instead of #pragma unroll: the rows must stay in registers, and the unroller gives up on the long
+// inner loops of the first pairs, which would put the array into local memory)
 template <int K>
-__device__ __forceinline__ void pair_update(double (&a)[32], double (&r)[32], const PairXch* nxt, double l0, double l1,
-                                            double w0, double w1) {
+__device__ __forceinline__ void pair_update(double (&a)[32], const PairXch* nxt, double l0, double l1) {
     if constexpr (K < 32) {
         const double2 c = *reinterpret_cast<const double2*>(&nxt[K].l0);  // (L[K][j], L[K][j+1]): broadcast load
         a[K] = fma(-l1, c.y, fma(-l0, c.x, a[K]));
-        r[K] = fma(-c.y, w1, fma(-c.x, w0, r[K]));
-        pair_update<K + 1>(a, r, nxt, l0, l1, w0, w1);
+        pair_update<K + 1>(a, nxt, l0, l1);
     }
 }
 
+// One pair of columns.  Every lane applies the same formulas: for the block's own rows they reproduce l00, l10 and l11
+// (lane J holds d0 in a[J]; lane J + 1 holds b and d1), rows above the block compute garbage that nobody reads and that
+// is masked when the columns are stored -- straight-line code.
 template <int J>
-__device__ __forceinline__ void pair_step(double (&a)[32], double (&r)[32], double& piv, double d0, double d1, double b,
-                                          PairXch* xch, double* D, int ld, double* Winv, int32_t* info, int base, int lane) {
+__device__ __forceinline__ void pair_step(double (&a)[32], double& piv, const PairScal sc, int& fail, PairXch* xch, double* D,
+                                          int ld, double* rdiag, unsigned long long* bars, int lane) {
     if constexpr (J < 32) {
-        const double b2 = b * b;
-        const double det = fma(d0, d1, -b2) - fma(b, b, -b2);  // d0 d1 - b^2 with the rounding of b^2 compensated
-        if (lane == 0 && info) {
-            if (!(d0 > 0.0)) atomicCAS(info, 0, base + J + 1);
-            else if (!(det > 0.0)) atomicCAS(info, 0, base + J + 2);
-        }
-        const double r0 = rsqrt_pivot(d0), rdet = rsqrt_pivot(det);
-        const double l00 = d0 * r0;            // sqrt(d0)
-        const double l10 = b * r0;
-        const double l11 = (det * rdet) * r0;  // sqrt(d1 - b^2 / d0)
-        const double r1 = rdet * l00;          // 1 / l11
-        double l0, l1;
-        if (lane > J + 1) {
-            l0 = a[J] * r0;
-            l1 = fma(-l0, l10, a[J + 1]) * r1;
-        } else {
-            l0 = (lane == J) ? l00 : ((lane == J + 1) ? l10 : 0.0);
-            l1 = (lane == J + 1) ? l11 : 0.0;
-        }
+        const double l0 = a[J] * sc.r0;
+        const double l1 = fma(-l0, sc.l10, a[J + 1]) * sc.r1;
         piv = fma(-l1, l1, fma(-l0, l0, piv));
         PairXch* nxt = xch + (((J >> 1) + 1) & 1) * 32;
         {
@@ -775,33 +795,27 @@ __device__ __forceinline__ void pair_step(double (&a)[32], double (&r)[32], doub
             if constexpr (J + 2 < 32) e.sub = a[J + 2]; else e.sub = 0.0;
             nxt[lane] = e;
         }
-        // columns J, J + 1 of L and rows J, J + 1 of W are final: back to shared memory at once (frees their registers)
-        *reinterpret_cast<double2*>(D + lane * ld + J) = make_double2(l0, l1);
-        const double w0 = r[J] * r0;
-        const double w1 = fma(-l10, w0, r[J + 1]) * r1;
-        Winv[J * SLD + lane] = w0;
-        Winv[(J + 1) * SLD + lane] = w1;
+        // columns J, J + 1 of L are final: back to shared memory at once (frees their registers, feeds the inverting warp)
+        *reinterpret_cast<double2*>(D + lane * ld + J) = make_double2(lane >= J ? l0 : 0.0, lane > J ? l1 : 0.0);
+        if (lane == 0) *reinterpret_cast<double2*>(rdiag + J) = make_double2(sc.r0, sc.r1);
+        mbar_arrive(bars + (J >> 1));  // all 32 lanes: each releases its own row's stores
         __syncwarp();
-        double nd0 = 0.0, nd1 = 0.0, nb = 0.0;
+        PairScal nsc{};
         if constexpr (J + 3 < 32) {
             const PairXch p2 = nxt[J + 2], p3 = nxt[J + 3];
-            nd0 = p2.piv;
-            nd1 = p3.piv;
-            nb = fma(-p3.l1, p2.l1, fma(-p3.l0, p2.l0, p3.sub));
+            nsc = pivot_block(p2.piv, p3.piv, fma(-p3.l1, p2.l1, fma(-p3.l0, p2.l0, p3.sub)), J + 2, fail);
         }
-        pair_update<J + 2>(a, r, nxt, l0, l1, w0, w1);
-        pair_step<J + 2>(a, r, piv, nd0, nd1, nb, xch, D, ld, Winv, info, base, lane);
+        pair_update<J + 2>(a, nxt, l0, l1);
+        pair_step<J + 2>(a, piv, nsc, fail, xch, D, ld, rdiag, bars, lane);
     }
 }
 
-__device__ __forceinline__ void warp_potrf32(double* D, int ld, double* Winv, double* xch_sm, int32_t* info, int base, int lane) {
+__device__ __noinline__ void warp_factor32(double* D, int ld, double* xch_sm, double* rdiag, unsigned long long* bars,
+                                              int32_t* info, int base, int lane) {
     PairXch* xch = reinterpret_cast<PairXch*>(xch_sm);  // 2 x 32 entries, double-buffered
-    double a[32], r[32];
+    double a[32];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-        a[c] = (c <= lane) ? D[lane * ld + c] : 0.0;
-        r[c] = (c == lane) ? 1.0 : 0.0;
-    }
+    for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? D[lane * ld + c] : 0.0;
     double piv = D[lane * ld + lane];
     {
         PairXch e;
@@ -809,9 +823,44 @@ __device__ __forceinline__ void warp_potrf32(double* D, int ld, double* Winv, do
         xch[lane] = e;
     }
     __syncwarp();
-    pair_step<0>(a, r, piv, xch[0].piv, xch[1].piv, xch[1].sub, xch, D, ld, Winv, info, base, lane);
+    int fail = 0;
+    const PairScal sc = pivot_block(xch[0].piv, xch[1].piv, xch[1].sub, 0, fail);
+    pair_step<0>(a, piv, sc, fail, xch, D, ld, rdiag, bars, lane);
+    if (lane == 0 && info && fail) atomicCAS(info, 0, base + fail);
     POTF2_STAMP(13);
-    __syncwarp();
+}
+
+template <int K>
+__device__ __forceinline__ void inv_update(double (&r)[32], const double* Dj, int ld, double w0, double w1) {
+    if constexpr (K < 32) {
+        const double2 c = *reinterpret_cast<const double2*>(Dj + K * ld);  // (L[K][j], L[K][j+1]): broadcast load
+        r[K] = fma(-c.y, w1, fma(-c.x, w0, r[K]));
+        inv_update<K + 1>(r, Dj, ld, w0, w1);
+    }
+}
+
+template <int J>
+__device__ __forceinline__ void inv_step(double (&r)[32], const double* D, int ld, double* Winv, const double* rdiag,
+                                         unsigned long long* bars, int parity, int lane) {
+    if constexpr (J < 32) {
+        mbar_wait(bars + (J >> 1), parity);
+        const double2 rd = *reinterpret_cast<const double2*>(rdiag + J);  // (1 / L[J][J], 1 / L[J+1][J+1])
+        const double l10 = D[(J + 1) * ld + J];
+        const double w0 = r[J] * rd.x;
+        const double w1 = fma(-l10, w0, r[J + 1]) * rd.y;
+        Winv[J * SLD + lane] = w0;
+        Winv[(J + 1) * SLD + lane] = w1;
+        inv_update<J + 2>(r, D + J, ld, w0, w1);
+        inv_step<J + 2>(r, D, ld, Winv, rdiag, bars, parity, lane);
+    }
+}
+
+__device__ __noinline__ void warp_inverse32(const double* D, int ld, double* Winv, const double* rdiag, unsigned long long* bars,
+                                               int parity, int lane) {
+    double r[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) r[c] = (c == lane) ? 1.0 : 0.0;
+    inv_step<0>(r, D, ld, Winv, rdiag, bars, parity, lane);
     POTF2_STAMP(14);
 }
 
@@ -822,28 +871,35 @@ __device__ __forceinline__ void warp_potrf32(double* D, int ld, double* Winv, do
 __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double* invd, int32_t* info, int base, PeerTiles peers) {
     extern __shared__ __align__(16) double sm[];
     double* scratch = sm + PT * PLD;
-    double* rdiag = scratch + N_SCRATCH * 32 * SLD;  // exchange area of warp_potrf32: 2 x 32 x 4 doubles
+    double* xch = scratch + N_SCRATCH * 32 * SLD;    // exchange area of warp_factor32: 2 x 32 x 4 doubles
+    double* rdiag = xch + 2 * 32 * 4;                 // 1 / L_ii of the block being factored
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(rdiag + 32);  // one mbarrier per column pair of a block
+    if (threadIdx.x < 16) mbar_init(bars + threadIdx.x, 32);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     POTF2_STAMP(0);
-    // tile -> shared memory (16-byte asynchronous copies, all in flight at once), then zero the strict upper triangle
+    // lower 32 x 32 blocks of the tile -> shared memory (16-byte asynchronous copies, all in flight at once).  The strictly
+    // upper blocks are never read, except (0,1) and (2,3) by the products of the inverse: those are zeroed; the upper
+    // triangles of the diagonal blocks are zeroed by the factoring warp when it writes the columns back.
 #pragma unroll 8
     for (int c = tid; c < PT * PT / 2; c += 256) {
         const int i = c >> 6, j2 = (c & 63) * 2;
-        cp_async16(sm + i * PLD + j2, A + (int64_t)i * ld + j2);
+        if ((j2 >> 5) <= (i >> 5)) cp_async16(sm + i * PLD + j2, A + (int64_t)i * ld + j2);
     }
     cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-    for (int e = tid; e < PT * PT; e += 256) {
-        const int i = e >> 7, j = e & 127;
-        if (j > i) sm[i * PLD + j] = 0.0;
+    for (int e = tid; e < 2 * 32 * 32; e += 256) {
+        const int half = e >> 10, i = (e >> 5) & 31, j = e & 31;
+        sm[(64 * half + i) * PLD + 64 * half + 32 + j] = 0.0;
     }
+    cp_async_wait<0>();
     __syncthreads();
     POTF2_STAMP(1);
     // kb = -1: factor block 0; kb >= 0: panel kb, then the trailing update of which warp 0 takes the next diagonal block
-    // (strips 0-3 of column group 0) and factors it at once while warps 1-7 update the rest.  (One call site of
-    // warp_potrf32: its straight-line code is ~60 KB and a second copy would thrash the instruction cache.)
-    for (int kb = -1; kb < 3; ++kb) {
+    // (strips 0-3 of column group 0) and factors it at once while warps 1-7 update the rest; warp 1 then inverts the block
+    // behind the factoring warp.  (One call site of the factor / inverse: their straight-line code is ~50 KB, a second copy
+    // would thrash the instruction cache -- the loop start is opaque so that the first iteration is not peeled.)
+    const int kb_first = (ld < 0) ? 0 : -1;
+#pragma unroll 1
+    for (int kb = kb_first; kb < 3; ++kb) {
         const int o = 32 * kb;
         const int r_lo = o + 32;
         const int n_strips = (PT - r_lo) / 8;
@@ -857,6 +913,7 @@ __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double*
             __syncthreads();
         }
         POTF2_STAMP(3 + 2 * kb);
+        double* Dblk = sm + r_lo * PLD + r_lo;
         if (warp == 0) {
             if (kb >= 0) {
                 for (int st = 0; st < 4; ++st)
@@ -864,31 +921,35 @@ __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double*
                                          sm + r_lo * PLD + o, PLD, -1.0, true, st + 1, lane);
                 __syncwarp();
             }
-            warp_potrf32(sm + r_lo * PLD + r_lo, PLD, scratch + (kb + 1) * 32 * SLD, rdiag, info, base + r_lo, lane);
-        } else if (kb >= 0) {
-            // trailing update (lower): tasks = (8-row strip, 32-column group at or left of it)
-            int task = 0;
-            for (int st = 4; st < n_strips; ++st) {
-                const int n_groups = st / 4 + 1;
-                for (int cg = 0; cg < n_groups; ++cg, ++task) {
-                    if (task % 7 != warp - 1) continue;
-                    const int r0 = r_lo + st * 8, c0 = r_lo + cg * 32;
-                    const int n_tiles = min(4, (r0 - c0) / 8 + 1);  // tiles at or left of the diagonal tile
-                    strip_mma<false, 32>(sm + r0 * PLD + c0, PLD, sm + r0 * PLD + o, PLD, sm + c0 * PLD + o, PLD, -1.0, true,
-                                         n_tiles, lane);
+            warp_factor32(Dblk, PLD, xch, rdiag, bars, info, base + r_lo, lane);
+        } else {
+            if (kb >= 0) {
+                // trailing update (lower): tasks = (8-row strip, 32-column group at or left of it)
+                int task = 0;
+                for (int st = 4; st < n_strips; ++st) {
+                    const int n_groups = st / 4 + 1;
+                    for (int cg = 0; cg < n_groups; ++cg, ++task) {
+                        if (task % 7 != warp - 1) continue;
+                        const int r0 = r_lo + st * 8, c0 = r_lo + cg * 32;
+                        const int n_tiles = min(4, (r0 - c0) / 8 + 1);  // tiles at or left of the diagonal tile
+                        strip_mma<false, 32>(sm + r0 * PLD + c0, PLD, sm + r0 * PLD + o, PLD, sm + c0 * PLD + o, PLD, -1.0, true,
+                                             n_tiles, lane);
+                    }
                 }
             }
+            if (warp == 1) warp_inverse32(Dblk, PLD, scratch + (kb + 1) * 32 * SLD, rdiag, bars, (kb + 1) & 1, lane);
         }
         __syncthreads();
         POTF2_STAMP(4 + 2 * kb);
     }
     POTF2_STAMP(9);
-    // L -> global (16-byte stores); peers get the diagonal only
+    // L -> global (16-byte stores, zeros above the diagonal); peers get the diagonal only
+#pragma unroll 8
     for (int c = tid; c < PT * PT / 2; c += 256) {
         const int i = c >> 6, j2 = (c & 63) * 2;
-        double2 v;
-        v.x = (j2 <= i) ? sm[i * PLD + j2] : 0.0;
-        v.y = (j2 + 1 <= i) ? sm[i * PLD + j2 + 1] : 0.0;
+        double2 v = *reinterpret_cast<const double2*>(sm + i * PLD + j2);
+        if (j2 > i) v.x = 0.0;
+        if (j2 + 1 > i) v.y = 0.0;
         *reinterpret_cast<double2*>(A + (int64_t)i * ld + j2) = v;
     }
     if (tid < PT) {
@@ -915,26 +976,33 @@ __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double*
         sm[(32 * kb + i) * PLD + 32 * kb + j] = scratch[kb * 32 * SLD + i * SLD + j];
     }
     __syncthreads();
-    // Step 3: T = L21 W11 into the upper-right quadrant; 16 tasks (8 strips x 2 column groups)
-    for (int task = warp; task < 16; task += 8) {
-        const int st = task >> 1, cg = task & 1;
-        strip_mma<true, 64>(sm + (st * 8) * PLD + 64 + cg * 32, PLD, sm + (64 + st * 8) * PLD, PLD, sm + cg * 32, PLD, 1.0,
-                            false, 4, lane);
+    // Step 3: T = L21 W11 into the upper-right quadrant; 16 tasks (8 strips x 2 column groups).  W11 is lower triangular:
+    // its second column group only has rows k >= 32.  Every warp takes one task of each kind.
+    {
+        const int st = warp;
+        strip_mma<true, 64>(sm + (st * 8) * PLD + 64, PLD, sm + (64 + st * 8) * PLD, PLD, sm, PLD, 1.0, false, 4, lane);
+        strip_mma<true, 32>(sm + (st * 8) * PLD + 96, PLD, sm + (64 + st * 8) * PLD + 32, PLD, sm + 32 * PLD + 32, PLD, 1.0, false, 4, lane);
     }
     __syncthreads();
-    // Step 4: W21 = -W22 T
-    for (int task = warp; task < 16; task += 8) {
-        const int st = task >> 1, cg = task & 1;
-        strip_mma<true, 64>(sm + (64 + st * 8) * PLD + cg * 32, PLD, sm + (64 + st * 8) * PLD + 64, PLD, sm + 64 + cg * 32, PLD,
-                            -1.0, false, 4, lane);
+    // Step 4: W21 = -W22 T.  W22 is lower triangular: its first four row strips only have columns k < 32.  Warp w takes
+    // strip w for the first column group and strip 7 - w for the second (one short and one long product each).
+#pragma unroll
+    for (int cg = 0; cg < 2; ++cg) {
+        const int st = cg == 0 ? warp : 7 - warp;
+        double* C = sm + (64 + st * 8) * PLD + cg * 32;
+        const double* Aw = sm + (64 + st * 8) * PLD + 64;
+        const double* Bt = sm + 64 + cg * 32;
+        if (st < 4) strip_mma<true, 32>(C, PLD, Aw, PLD, Bt, PLD, -1.0, false, 4, lane);
+        else strip_mma<true, 64>(C, PLD, Aw, PLD, Bt, PLD, -1.0, false, 4, lane);
     }
     __syncthreads();
     POTF2_STAMP(11);
+#pragma unroll 8
     for (int c = tid; c < PT * PT / 2; c += 256) {
         const int i = c >> 6, j2 = (c & 63) * 2;
-        double2 v;
-        v.x = (j2 <= i) ? sm[i * PLD + j2] : 0.0;
-        v.y = (j2 + 1 <= i) ? sm[i * PLD + j2 + 1] : 0.0;
+        double2 v = *reinterpret_cast<const double2*>(sm + i * PLD + j2);
+        if (j2 > i) v.x = 0.0;
+        if (j2 + 1 > i) v.y = 0.0;
         *reinterpret_cast<double2*>(invd + i * PT + j2) = v;
         if (j2 <= i)
             for (int p = 0; p < peers.n; ++p) *reinterpret_cast<double2*>(peers.invd[p] + i * PT + j2) = v;
