@@ -192,7 +192,8 @@ int pigp_adam_host(pigp_solver* s, const double* theta0_host, const double* y_ho
 /* --- building blocks exposed for tests and benchmarks (device pointers, n multiple of PIGP_TILE) --- */
 /* In-place lower Cholesky of the leading n x n of A (row-major, ld), applying L^-T to the m_extra rows below it
  * (jnp.linalg.cholesky + jnp.linalg.solve of GP/gp.py:83-84, :106-118).  invd_dev: n/128 inverse diagonal tiles
- * (128*128 doubles each), workspace output. */
+ * (128*128 doubles each), workspace output.  Only the lower triangle of A is defined on output (the part above the
+ * diagonal is not referenced by any consumer and is left partly overwritten). */
 int pigp_potrf_lower(double* A_dev, int64_t ld, int64_t n, int64_t m_extra, double* invd_dev,
                      int32_t* info_dev, void* stream);
 /* K^-1 (lower triangle, into X_dev) from the factor L (lower of L_dev) -- replaces solve(L.T, solve(L, I)),

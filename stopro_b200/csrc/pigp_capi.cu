@@ -521,7 +521,7 @@ static int trsm_rec(double* V, int64_t ldv, int64_t m, const FactorView& f, int 
         g.B = f.invd + (int64_t)c0 * TILE * TILE; g.ldb = TILE; g.b_kcontig = 1;
         g.C = V + (int64_t)c0 * TILE; g.ldc = ldv;
         g.force_bn128 = 1;  // in place: a CTA reads its 128 columns of its rows before it writes them
-        g.Lkk = f.L + (int64_t)c0 * TILE * f.ld + (int64_t)c0 * TILE; g.ldl = f.ld;  // refined (see k_trsm_refine)
+        g.Lkk = f.L + (int64_t)c0 * TILE * f.ld + (int64_t)c0 * TILE; g.ldl = f.ld;  // block substitution with refinement (k_trsm_blk)
         return launch_gemm(g, st);
     }
     const int n1 = nt / 2, n2 = nt - n1;

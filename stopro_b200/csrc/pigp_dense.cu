@@ -9,7 +9,9 @@
 //   tcgen05 has no f64 kind).  Either index of A / B may be the contiguous one, k-ranges can follow a triangular
 //   operand tile by tile and tiles above the diagonal can be skipped, so that the same kernel is the SYRK/GEMM
 //   trailing update of the Cholesky, the TRSM-by-inverse, both TRTRI products and the LAUUM.
-// * k_potf2: one CTA factors a 128 x 128 diagonal tile in shared memory and inverts the factor in place.
+// * k_potf2: one CTA factors a 128 x 128 diagonal tile in shared memory (32 x 32 blocks: one warp eliminates column pairs,
+//   a second warp inverts the block behind it); k_tile_inv completes inverse tiles off the critical path.
+// * k_trsm_blk: the panel solve X = A inv(L_kk)^T by block forward substitution with refined 32 x 32 diagonal solves.
 // * Host drivers: recursive right-looking Cholesky (all flops in k_gemm), TRTRI + LAUUM for K^-1.
 #include <algorithm>
 #include <cstdlib>
@@ -398,153 +400,175 @@ static int launch_gemm_small(const GemmDesc& d, cudaStream_t st) {
     return PIGP_OK;
 }
 
-// ----------------------------------------------------------------------------------------------- refined TRSM
-// X = A inv(Lkk)^T for 64-row slabs of a 128-column panel, in place, with one step of iterative refinement:
-//   X0 = A W^T,  R = A - X0 Lkk^T,  X = X0 + R W^T      (W = inv(Lkk) from k_potf2, B operand of the descriptor).
-// The explicit inverse of an ill-conditioned diagonal tile only satisfies |W Lkk - I| ~ n u cond(Lkk); one refinement
-// step squares that residual, which restores the row-wise backward stability of a substitution-based TRSM
-// (LAPACK-grade factorisation: backward error ~1e-16 instead of ~1e-13 on the cond(K) = 1e10 sinusoidal matrix).
-// One CTA per slab: the slab lives in shared memory for the three products, W / Lkk stream through a cp.async pipeline.
-constexpr int TR_SLD = 128 + 8, TR_STAGES = 3;
-__host__ __device__ constexpr int tr_smem(int bm) { return (2 * bm * TR_SLD + TR_STAGES * 128 * LDS_K) * (int)sizeof(double); }
+// ----------------------------------------------------------------------------------------------- block TRSM
+// X = A inv(Lkk)^T for TR_BM-row slabs of a 128-column panel, in place, by forward substitution over the four 32-column
+// blocks of Lkk, each diagonal solve done with the block's explicit inverse plus one refinement step:
+//   T_j = A_j - sum_{i<j} X_i L_ji^T;   X0 = T_j W_j^T,  R = T_j - X0 L_jj^T,  X_j = X0 + R W_j^T      (W_j = inv(L_jj))
+// Only the diagonal 32 x 32 blocks of the inverse tile are read (k_potf2 produces exactly those on the critical path; the
+// rest of the tile is completed off it by k_tile_inv).  Against three full 128-deep products this is 2.7 x fewer flops, and
+// the refinement acts on blocks whose condition number is far below the tile's: row-wise backward stable like LAPACK's
+// substitution.  One CTA per slab, everything in shared memory after one wave of asynchronous copies; each of the 15
+// barrier-separated phases is a K = 32..96 product of 8 x 8 DMMA tiles spread over the warps (all four tensor pipes).
+constexpr int TB_SLD = 132, TB_LD = 36;  // row strides = 4 mod 16 doubles: conflict-free 8-byte fragment loads
+__host__ __device__ constexpr int tb_smem(int bm) { return (bm * TB_SLD + 5 * bm * TB_LD + 14 * 32 * TB_LD) * (int)sizeof(double); }
 
-// Warp layout of a TR_BM x 128 slab: TR_WM warps along the rows (8 * TR_MI rows each), 8 / TR_WM along the columns
-// (8 * TR_NI columns each).  TR_BM = 8 / 16 keep the per-CTA DMMA chain short for the latency-bound panels of small N.
-template <int TR_BM> struct TrShape {
-    static constexpr int WM = TR_BM >= 16 ? 2 : 1, WN = 8 / WM;
-    static constexpr int MI = TR_BM / (8 * WM), NI = 16 / WN;
-};
-
-template <int TR_BM>
-__device__ __forceinline__ void trsm_stage(const double* S, const double* Bg, int64_t ldb, double* sB,
-                                           double (&acc)[TrShape<TR_BM>::MI][TrShape<TR_BM>::NI][2], int tid, int wm, int wn, int gid, int tig) {
-    using Sh = TrShape<TR_BM>;
-    constexpr int TR_MI = Sh::MI, TR_NI = Sh::NI;
+// (d, e) += A[row gid][k..k+K) * B[col gid][k..k+K)^T as four independent DMMA chains (two per accumulator pair)
+template <int K>
+__device__ __forceinline__ void tile_mma(double (&d)[2], double (&e)[2], const double* Arow, const double* Brow, int tig) {
+    double a[K / 4], b[K / 4];
 #pragma unroll
-    for (int i = 0; i < TR_MI; ++i)
-#pragma unroll
-        for (int j = 0; j < TR_NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    constexpr int NK = 128 / BK, OPB = 128 * LDS_K;
-#pragma unroll
-    for (int s = 0; s < TR_STAGES - 1; ++s) {
-        load_operand<true, 128, 256>(sB + s * OPB, Bg, ldb, 0, (int64_t)s * BK, tid);
-        cp_async_commit();
+    for (int q = 0; q < K / 4; ++q) {
+        a[q] = Arow[4 * q + tig];
+        b[q] = Brow[4 * q + tig];
     }
-    for (int it = 0; it < NK; ++it) {
-        cp_async_wait<TR_STAGES - 2>();
-        __syncthreads();
-        {
-            const int nx = it + TR_STAGES - 1;
-            if (nx < NK) load_operand<true, 128, 256>(sB + (nx % TR_STAGES) * OPB, Bg, ldb, 0, (int64_t)nx * BK, tid);
-            cp_async_commit();
-        }
-        const double* b = sB + (it % TR_STAGES) * OPB;
+    double f[2] = {0.0, 0.0}, h[2] = {0.0, 0.0};
 #pragma unroll
-        for (int k8 = 0; k8 < BK; k8 += 8) {
-            double2 af[TR_MI], bf[TR_NI];
-#pragma unroll
-            for (int mi = 0; mi < TR_MI; ++mi)
-                af[mi] = *reinterpret_cast<const double2*>(S + (wm * 8 * TR_MI + 8 * mi + gid) * TR_SLD + it * BK + k8 + 2 * tig);
-            load_frags<true, TR_NI, 128>(bf, b, wn * 8 * TR_NI, k8, gid, tig);
-#pragma unroll
-            for (int mi = 0; mi < TR_MI; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < TR_NI; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi].x, bf[ni].x);
-#pragma unroll
-            for (int mi = 0; mi < TR_MI; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < TR_NI; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], af[mi].y, bf[ni].y);
-        }
+    for (int q = 0; q < K / 4; q += 4) {
+        dmma(d[0], d[1], a[q], b[q]);
+        dmma(e[0], e[1], a[q + 1], b[q + 1]);
+        dmma(f[0], f[1], a[q + 2], b[q + 2]);
+        dmma(h[0], h[1], a[q + 3], b[q + 3]);
     }
-    cp_async_wait<0>();
-    __syncthreads();  // every warp is done with S and the pipeline buffers
+    d[0] += f[0]; d[1] += f[1];
+    e[0] += h[0]; e[1] += h[1];
 }
 
 template <int TR_BM>
-__global__ void __launch_bounds__(256) k_trsm_refine(GemmDesc g) {
-    using Sh = TrShape<TR_BM>;
-    constexpr int TR_MI = Sh::MI, TR_NI = Sh::NI;
+__global__ void __launch_bounds__(256) k_trsm_blk(GemmDesc g) {
+    constexpr int N_TILES = TR_BM / 8 * 4;                 // 8 x 8 tiles of one TR_BM x 32 block
+    constexpr int TPW = N_TILES >= 8 ? N_TILES / 8 : 1;    // tiles per warp
     extern __shared__ __align__(16) double smem[];
-    double* S0 = smem;                       // A, later the residual R
-    double* S1 = S0 + TR_BM * TR_SLD;        // X0
-    double* sB = S1 + TR_BM * TR_SLD;
+    double* S = smem;                         // TR_BM x 128: A, then per block T / R
+    double* Xb = S + TR_BM * TB_SLD;          // 4 solved blocks, TR_BM x 32 each
+    double* X0 = Xb + 4 * TR_BM * TB_LD;      // TR_BM x 32
+    double* Ls = X0 + TR_BM * TB_LD;          // blocks (jb, ib <= jb) of Lkk at index jb (jb + 1) / 2 + ib, 32 x 32 each
+    double* Ws = Ls + 10 * 32 * TB_LD;        // the four diagonal blocks of inv(Lkk)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
-    const int wm = warp % Sh::WM, wn = warp / Sh::WM;
     constexpr int SUB = BM / TR_BM;
     const int tm = blockIdx.x;
     const int64_t m0 = (int64_t)(tm / SUB) * g.m_ts * BM + (tm % SUB) * TR_BM;
     wait_flags(g, tid);
-    // slab -> S0 (16-byte asynchronous copies)
+    // one group of asynchronous copies per column block: what step jb needs (its 32 columns of the slab, row jb of the
+    // blocks of Lkk, W_jb) arrives while steps 0 .. jb - 1 compute
+#pragma unroll
+    for (int jb = 0; jb < 4; ++jb) {
+        for (int c = tid; c < TR_BM * 16; c += 256) {
+            const int r = c >> 4, ch = (c & 15) * 2;
+            cp_async16(S + r * TB_SLD + 32 * jb + ch, g.A + (m0 + r) * g.lda + 32 * jb + ch);
+        }
+        for (int c = tid; c < (jb + 2) * 512; c += 256) {
+            const int ib = c >> 9, r = (c >> 4) & 31, ch = (c & 15) * 2;
+            if (ib <= jb) cp_async16(Ls + ((jb * (jb + 1) / 2 + ib) * 32 + r) * TB_LD + ch, g.Lkk + (int64_t)(32 * jb + r) * g.ldl + 32 * ib + ch);
+            else cp_async16(Ws + (jb * 32 + r) * TB_LD + ch, g.B + (int64_t)(32 * jb + r) * g.ldb + 32 * jb + ch);
+        }
+        cp_async_commit();
+    }
+    const bool active = warp * TPW < N_TILES;
+    const int rt = (warp * TPW) >> 2, ct0 = (warp * TPW) & 3;  // this warp's tiles: row tile rt, column tiles ct0 .. ct0 + TPW
+    const int row = 8 * rt + gid;
+#pragma unroll
+    for (int jb = 0; jb < 4; ++jb) {
+        double* Sj = S + 32 * jb;  // block jb of the slab
+        if (jb == 0) cp_async_wait<3>();
+        else if (jb == 1) cp_async_wait<2>();
+        else if (jb == 2) cp_async_wait<1>();
+        else cp_async_wait<0>();
+        __syncthreads();
+        if (jb > 0) {
+            // T_j = A_j - sum_{i<j} X_i L_ji^T
+            if (active) {
+#pragma unroll
+                for (int t = 0; t < TPW; ++t) {
+                    const int ct = ct0 + t;
+                    double d[2] = {0.0, 0.0}, e[2] = {0.0, 0.0};
+#pragma unroll
+                    for (int i = 0; i < jb; ++i)
+                        tile_mma<32>(d, e, Xb + (i * TR_BM + row) * TB_LD, Ls + ((jb * (jb + 1) / 2 + i) * 32 + 8 * ct + gid) * TB_LD, tig);
+                    double2* p = reinterpret_cast<double2*>(Sj + row * TB_SLD + 8 * ct + 2 * tig);
+                    double2 v = *p;
+                    v.x -= d[0] + e[0];
+                    v.y -= d[1] + e[1];
+                    *p = v;
+                }
+            }
+            __syncthreads();
+        }
+        const double* Wj = Ws + jb * 32 * TB_LD;
+        const double* Ljj = Ls + (jb * (jb + 1) / 2 + jb) * 32 * TB_LD;
+        // X0 = T_j W_j^T
+        if (active) {
+#pragma unroll
+            for (int t = 0; t < TPW; ++t) {
+                const int ct = ct0 + t;
+                double d[2] = {0.0, 0.0}, e[2] = {0.0, 0.0};
+                tile_mma<32>(d, e, Sj + row * TB_SLD, Wj + (8 * ct + gid) * TB_LD, tig);
+                *reinterpret_cast<double2*>(X0 + row * TB_LD + 8 * ct + 2 * tig) = make_double2(d[0] + e[0], d[1] + e[1]);
+            }
+        }
+        __syncthreads();
+        // R = T_j - X0 L_jj^T (in place of T_j: a warp only reads its own tiles of T_j here)
+        if (active) {
+#pragma unroll
+            for (int t = 0; t < TPW; ++t) {
+                const int ct = ct0 + t;
+                double d[2] = {0.0, 0.0}, e[2] = {0.0, 0.0};
+                tile_mma<32>(d, e, X0 + row * TB_LD, Ljj + (8 * ct + gid) * TB_LD, tig);
+                double2* p = reinterpret_cast<double2*>(Sj + row * TB_SLD + 8 * ct + 2 * tig);
+                double2 v = *p;
+                v.x -= d[0] + e[0];
+                v.y -= d[1] + e[1];
+                *p = v;
+            }
+        }
+        __syncthreads();
+        // X_j = X0 + R W_j^T
+        if (active) {
+#pragma unroll
+            for (int t = 0; t < TPW; ++t) {
+                const int ct = ct0 + t;
+                double d[2] = {0.0, 0.0}, e[2] = {0.0, 0.0};
+                tile_mma<32>(d, e, Sj + row * TB_SLD, Wj + (8 * ct + gid) * TB_LD, tig);
+                const double2 x0 = *reinterpret_cast<const double2*>(X0 + row * TB_LD + 8 * ct + 2 * tig);
+                *reinterpret_cast<double2*>(Xb + (jb * TR_BM + row) * TB_LD + 8 * ct + 2 * tig) =
+                    make_double2(x0.x + d[0] + e[0], x0.y + d[1] + e[1]);
+            }
+        }
+        if (jb == 3) __syncthreads();  // (the other steps are followed by the barrier that opens the next one)
+    }
     for (int c = tid; c < TR_BM * 64; c += 256) {
         const int r = c >> 6, j2 = (c & 63) * 2;
-        cp_async16(S0 + r * TR_SLD + j2, g.A + (m0 + r) * g.lda + j2);
+        *reinterpret_cast<double2*>(g.C + (m0 + r) * g.ldc + j2) =
+            *reinterpret_cast<const double2*>(Xb + ((j2 >> 5) * TR_BM + r) * TB_LD + (j2 & 31));
     }
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-    double acc[TR_MI][TR_NI][2];
-    // X0 = A W^T -> S1
-    trsm_stage<TR_BM>(S0, g.B, g.ldb, sB, acc, tid, wm, wn, gid, tig);
-#pragma unroll
-    for (int mi = 0; mi < TR_MI; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < TR_NI; ++ni)
-            *reinterpret_cast<double2*>(S1 + (wm * 8 * TR_MI + 8 * mi + gid) * TR_SLD + wn * 8 * TR_NI + 8 * ni + 2 * tig) =
-                make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-    __syncthreads();
-    // R = A - X0 Lkk^T -> S0
-    trsm_stage<TR_BM>(S1, g.Lkk, g.ldl, sB, acc, tid, wm, wn, gid, tig);
-#pragma unroll
-    for (int mi = 0; mi < TR_MI; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < TR_NI; ++ni) {
-            double2* e = reinterpret_cast<double2*>(S0 + (wm * 8 * TR_MI + 8 * mi + gid) * TR_SLD + wn * 8 * TR_NI + 8 * ni + 2 * tig);
-            double2 a0 = *e;
-            a0.x -= acc[mi][ni][0]; a0.y -= acc[mi][ni][1];
-            *e = a0;
-        }
-    __syncthreads();
-    // X = X0 + R W^T -> global (in place)
-    trsm_stage<TR_BM>(S0, g.B, g.ldb, sB, acc, tid, wm, wn, gid, tig);
-#pragma unroll
-    for (int mi = 0; mi < TR_MI; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < TR_NI; ++ni) {
-            const int lr = wm * 8 * TR_MI + 8 * mi + gid, lc = wn * 8 * TR_NI + 8 * ni + 2 * tig;
-            const double2 x0 = *reinterpret_cast<const double2*>(S1 + lr * TR_SLD + lc);
-            *reinterpret_cast<double2*>(g.C + (m0 + lr) * g.ldc + lc) = make_double2(x0.x + acc[mi][ni][0], x0.y + acc[mi][ni][1]);
-        }
 }
 
 template <int TR_BM>
-static int launch_trsm_refine_t(const GemmDesc& d, cudaStream_t st) {
+static int launch_trsm_blk_t(const GemmDesc& d, cudaStream_t st) {
     static bool attr_done[64] = {};
     int dev = 0;
     PIGP_CUDA(cudaGetDevice(&dev));
     if (!attr_done[dev & 63]) {
-        PIGP_CUDA(cudaFuncSetAttribute(k_trsm_refine<TR_BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem(TR_BM)));
+        PIGP_CUDA(cudaFuncSetAttribute(k_trsm_blk<TR_BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, tb_smem(TR_BM)));
         attr_done[dev & 63] = true;
     }
     double flops = 0.0;
     if (g_prof_on) {
-        flops = 3.0 * 2.0 * d.M * 128.0 * 128.0;
+        flops = 18.0 * 2.0 * d.M * 32.0 * 32.0;
         prof_note(d.M, d.N, d.K, 200);
     }
     ProfScope prof(PROF_GEMM, st, flops);
-    k_trsm_refine<TR_BM><<<(unsigned)(d.M / TR_BM), 256, tr_smem(TR_BM), st>>>(d);
+    k_trsm_blk<TR_BM><<<(unsigned)(d.M / TR_BM), 256, tb_smem(TR_BM), st>>>(d);
     count_launch();
     return PIGP_OK;
 }
 
-// 64-row slabs halve the re-streaming of the 128 x 128 operands once the panel covers the GPU.  Shorter panels are latency
-// bound -- the three products of a slab run back to back on one SM's FP64 tensor pipe, 3 x 2 x rows x 128 x 128 flops at
-// ~126 flop/clk -- so the slab height shrinks with the panel until the CTAs no longer cover the 148 SMs.
-static int launch_trsm_refine(const GemmDesc& d, cudaStream_t st) {
-    if (d.M >= 148 * 64) return launch_trsm_refine_t<64>(d, st);
-    if (d.M > 148 * 16) return launch_trsm_refine_t<32>(d, st);
-    if (d.M > 148 * 8) return launch_trsm_refine_t<16>(d, st);
-    return launch_trsm_refine_t<8>(d, st);
+// Short panels are latency bound (the phases of a slab run back to back on one SM), so the slab height shrinks with the
+// panel until the CTAs no longer cover the 148 SMs.
+static int launch_trsm_blk(const GemmDesc& d, cudaStream_t st) {
+    if (d.M > 148 * 16) return launch_trsm_blk_t<32>(d, st);
+    if (d.M > 148 * 8) return launch_trsm_blk_t<16>(d, st);
+    return launch_trsm_blk_t<8>(d, st);
 }
 
 static int g_gemm_bn = 0;  // 0: read PIGP_GEMM_BN once (kernel tuning); 128 or 64
@@ -597,10 +621,10 @@ int launch_gemm(const GemmDesc& g_in, cudaStream_t st) {
     if (g.m_ts == 0) g.m_ts = 1;
     if (g.Lkk) {
         if (g.N != BM || g.K != BM || !g.a_kcontig || !g.b_kcontig || g.C != g.A || g.alpha != 1.0 || g.beta != 0.0) {
-            set_error("pigp gemm: the refined TRSM is in place with N = K = 128 and k-contiguous operands");
+            set_error("pigp gemm: the block TRSM is in place with N = K = 128 and k-contiguous operands");
             return PIGP_EINVAL;
         }
-        PIGP_TRY(launch_trsm_refine(g, st));
+        PIGP_TRY(launch_trsm_blk(g, st));
         PIGP_CUDA(cudaGetLastError());
         return PIGP_OK;
     }
@@ -868,7 +892,7 @@ __device__ __noinline__ void warp_inverse32(const double* D, int ld, double* Win
 // inv(L) (lower, zeros above) to invd[128*128].  Non-positive pivot -> *info = base + column + 1 (first one wins)
 // and NaNs propagate, which is what jnp.linalg.cholesky gives the reference.
 // Peers (multi-GPU) receive inv(L) and the diagonal of L -- what their TRSMs and their log-det read -- then the flag.
-__global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double* invd, int32_t* info, int base, PeerTiles peers) {
+__global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double* invd, int32_t* info, int base) {
     extern __shared__ __align__(16) double sm[];
     double* scratch = sm + PT * PLD;
     double* xch = scratch + N_SCRATCH * 32 * SLD;    // exchange area of warp_factor32: 2 x 32 x 4 doubles
@@ -914,13 +938,14 @@ __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double*
         }
         POTF2_STAMP(3 + 2 * kb);
         double* Dblk = sm + r_lo * PLD + r_lo;
+        if (kb >= 0 && warp < 4) {
+            // the next diagonal block first: its four 8-row strips go to warps 0-3, which meet at a named barrier
+            const int st = warp;
+            strip_mma<false, 32>(sm + (r_lo + st * 8) * PLD + r_lo, PLD, sm + (r_lo + st * 8) * PLD + o, PLD, sm + r_lo * PLD + o, PLD,
+                                 -1.0, true, st + 1, lane);
+            asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        }
         if (warp == 0) {
-            if (kb >= 0) {
-                for (int st = 0; st < 4; ++st)
-                    strip_mma<false, 32>(sm + (r_lo + st * 8) * PLD + r_lo, PLD, sm + (r_lo + st * 8) * PLD + o, PLD,
-                                         sm + r_lo * PLD + o, PLD, -1.0, true, st + 1, lane);
-                __syncwarp();
-            }
             warp_factor32(Dblk, PLD, xch, rdiag, bars, info, base + r_lo, lane);
         } else {
             if (kb >= 0) {
@@ -943,21 +968,61 @@ __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double*
         POTF2_STAMP(4 + 2 * kb);
     }
     POTF2_STAMP(9);
-    // L -> global (16-byte stores, zeros above the diagonal); peers get the diagonal only
+    // L -> global: the lower 32-blocks (16-byte stores; zeros above the diagonal inside the diagonal blocks).  The strictly
+    // upper blocks of the tile keep their input values: no kernel reads them, and a single SM's store path is ~32 B/clk
 #pragma unroll 8
     for (int c = tid; c < PT * PT / 2; c += 256) {
         const int i = c >> 6, j2 = (c & 63) * 2;
-        double2 v = *reinterpret_cast<const double2*>(sm + i * PLD + j2);
-        if (j2 > i) v.x = 0.0;
-        if (j2 + 1 > i) v.y = 0.0;
-        *reinterpret_cast<double2*>(A + (int64_t)i * ld + j2) = v;
-    }
-    if (tid < PT) {
-        const double v = sm[tid * PLD + tid];
-        for (int p = 0; p < peers.n; ++p) peers.a[p][(int64_t)tid * ld + tid] = v;
+        if ((j2 >> 5) <= (i >> 5)) {
+            double2 v = *reinterpret_cast<const double2*>(sm + i * PLD + j2);
+            if (j2 > i) v.x = 0.0;
+            if (j2 + 1 > i) v.y = 0.0;
+            *reinterpret_cast<double2*>(A + (int64_t)i * ld + j2) = v;
+        }
     }
     POTF2_STAMP(10);
-    // ---- inverse.  Step 1: off-diagonal 32-blocks of the two 64 x 64 halves, W_ba = -inv(L_b) (L_ba inv(L_a)).
+    // the four diagonal blocks of inv(L) -> invd: all that the block TRSM of the panel reads.  The rest of the inverse tile
+    // (needed by the L^-T products of the gradient only) is completed off the critical path by k_tile_inv.
+    for (int e = tid; e < 4 * 32 * 16; e += 256) {
+        const int kb = e >> 9, i = (e >> 4) & 31, j2 = (e & 15) * 2;
+        *reinterpret_cast<double2*>(invd + (32 * kb + i) * PT + 32 * kb + j2) =
+            *reinterpret_cast<const double2*>(scratch + (kb * 32 + i) * SLD + j2);
+    }
+    POTF2_STAMP(11);
+    POTF2_STAMP(12);
+}
+
+// Complete inverse diagonal tiles: W = inv(L_cc) from L_cc and the four diagonal 32 x 32 blocks of W that k_potf2 left in
+// invd[c] (one CTA per tile c = first + blockIdx.x * stride):
+//   the two 64 x 64 diagonal halves from their 32-blocks, W_ba = -inv(L_b) (L_ba inv(L_a)); then W21 = -W22 (L21 W11), with
+//   the (unused) upper-right 64 x 64 quadrant of the tile as scratch for L21 W11.
+// Optionally also writes the tile transposed into Yt (the diagonal tile of Y = L^-T, zeros below its diagonal).
+__global__ void __launch_bounds__(256, 1) k_tile_inv(const double* L, int64_t ld, double* invd, int first, int stride, double* Y, int64_t ldy) {
+    extern __shared__ __align__(16) double sm[];
+    double* scratch = sm + PT * PLD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = first + blockIdx.x * stride;
+    const double* Lcc = L + (int64_t)c * PT * ld + (int64_t)c * PT;
+    double* W = invd + (int64_t)c * PT * PT;
+    // sub-diagonal 32-blocks of L_cc -> tile; diagonal blocks of W -> scratch 0-3; blocks (0,1) and (2,3) of the tile are
+    // read by the products below and must be zero
+#pragma unroll 8
+    for (int q = tid; q < PT * PT / 2; q += 256) {
+        const int i = q >> 6, j2 = (q & 63) * 2;
+        if ((j2 >> 5) < (i >> 5)) cp_async16(sm + i * PLD + j2, Lcc + (int64_t)i * ld + j2);
+    }
+    for (int e = tid; e < 4 * 32 * 16; e += 256) {
+        const int kb = e >> 9, i = (e >> 4) & 31, j2 = (e & 15) * 2;
+        cp_async16(scratch + (kb * 32 + i) * SLD + j2, W + (32 * kb + i) * PT + 32 * kb + j2);
+    }
+    cp_async_commit();
+    for (int e = tid; e < 2 * 32 * 32; e += 256) {
+        const int half = e >> 10, i = (e >> 5) & 31, j = e & 31;
+        sm[(64 * half + i) * PLD + 64 * half + 32 + j] = 0.0;
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    // Step 1: off-diagonal 32-blocks of the two 64 x 64 halves, W_ba = -inv(L_b) (L_ba inv(L_a)).
     {
         const int half = warp >> 2, w4 = warp & 3;         // warps 0-3: blocks (1,0); warps 4-7: blocks (3,2)
         const int ra = 64 * half, rb = ra + 32;
@@ -996,23 +1061,37 @@ __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double*
         else strip_mma<true, 64>(C, PLD, Aw, PLD, Bt, PLD, -1.0, false, 4, lane);
     }
     __syncthreads();
-    POTF2_STAMP(11);
 #pragma unroll 8
-    for (int c = tid; c < PT * PT / 2; c += 256) {
-        const int i = c >> 6, j2 = (c & 63) * 2;
+    for (int q = tid; q < PT * PT / 2; q += 256) {
+        const int i = q >> 6, j2 = (q & 63) * 2;
         double2 v = *reinterpret_cast<const double2*>(sm + i * PLD + j2);
         if (j2 > i) v.x = 0.0;
         if (j2 + 1 > i) v.y = 0.0;
-        *reinterpret_cast<double2*>(invd + i * PT + j2) = v;
-        if (j2 <= i)
-            for (int p = 0; p < peers.n; ++p) *reinterpret_cast<double2*>(peers.invd[p] + i * PT + j2) = v;
+        *reinterpret_cast<double2*>(W + i * PT + j2) = v;
     }
-    if (peers.n > 0) {  // publish: every thread's peer stores are fenced, then one thread per peer releases the flag
-        __threadfence_system();
-        __syncthreads();
-        if (tid < peers.n) asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(peers.flag[tid]), "l"(peers.val) : "memory");
+    if (Y) {
+        double* Yt = Y + (int64_t)c * PT * ldy + (int64_t)c * PT;
+        for (int e = tid; e < PT * PT; e += 256) {
+            const int j = e >> 7, i = e & 127;  // Y[j][i] = W[i][j]
+            Yt[(int64_t)j * ldy + i] = (i >= j) ? sm[i * PLD + j] : 0.0;
+        }
     }
-    POTF2_STAMP(12);
+}
+
+int launch_tile_inv(const double* L, int64_t ld, double* invd, int first, int stride, int count, double* Y, int64_t ldy, cudaStream_t st) {
+    if (count <= 0) return PIGP_OK;
+    static bool attr_done[64] = {};
+    int dev = 0;
+    PIGP_CUDA(cudaGetDevice(&dev));
+    if (!attr_done[dev & 63]) {
+        PIGP_CUDA(cudaFuncSetAttribute(k_tile_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM));
+        attr_done[dev & 63] = true;
+    }
+    ProfScope prof(PROF_POTF2, st);
+    k_tile_inv<<<(unsigned)count, 256, POTF2_SMEM, st>>>(L, ld, invd, first, stride, Y, ldy);
+    count_launch();
+    PIGP_CUDA(cudaGetLastError());
+    return PIGP_OK;
 }
 
 int set_potf2_debug(long long* dev_buf) {
@@ -1020,7 +1099,7 @@ int set_potf2_debug(long long* dev_buf) {
     return PIGP_OK;
 }
 
-int launch_potf2(double* A, int64_t ld, double* invd, int32_t* info, int base, const PeerTiles& peers, cudaStream_t st) {
+int launch_potf2(double* A, int64_t ld, double* invd, int32_t* info, int base, cudaStream_t st) {
     static bool attr_done[64] = {};
     int dev = 0;
     PIGP_CUDA(cudaGetDevice(&dev));
@@ -1030,7 +1109,7 @@ int launch_potf2(double* A, int64_t ld, double* invd, int32_t* info, int base, c
         attr_set = true;
     }
     ProfScope prof(PROF_POTF2, st);
-    k_potf2<<<1, 256, POTF2_SMEM, st>>>(A, ld, invd, info, base, peers);
+    k_potf2<<<1, 256, POTF2_SMEM, st>>>(A, ld, invd, info, base);
     count_launch();
     PIGP_CUDA(cudaGetLastError());
     return PIGP_OK;
@@ -1040,7 +1119,7 @@ int launch_potf2(double* A, int64_t ld, double* invd, int32_t* info, int base, c
 static int chol_rec(double* A, int64_t ld, int64_t n, int64_t m_below, double* invd, int32_t* info, int base,
                     cudaStream_t st) {
     if (n == TILE) {
-        PIGP_TRY(launch_potf2(A, ld, invd, info, base, PeerTiles{}, st));
+        PIGP_TRY(launch_potf2(A, ld, invd, info, base, st));
         if (m_below > 0) {
             // B <- B * inv(L)^T, in place: every CTA reads its own 128 rows completely before writing them
             GemmDesc g{};
@@ -1076,7 +1155,9 @@ int potrf_lower(double* A, int64_t ld, int64_t n, int64_t m_extra, double* invd,
         set_error("pigp potrf: n and m_extra must be multiples of 128 and ld even");
         return PIGP_EINVAL;
     }
-    return chol_rec(A, ld, n, m_extra, invd, info, 0, st);
+    PIGP_TRY(chol_rec(A, ld, n, m_extra, invd, info, 0, st));
+    // the factorisation leaves the diagonal 32-blocks of the inverse tiles; callers of this entry point get complete tiles
+    return launch_tile_inv(A, ld, invd, 0, 1, (int)(n / TILE), nullptr, 0, st);
 }
 
 // ----------------------------------------------------------------------------------------------- TRTRI + LAUUM
@@ -1260,18 +1341,18 @@ int preload_dense() {
     PIGP_PRELOAD((k_gemm_s<32, 128, 3>));
     PIGP_PRELOAD((k_gemm_s<64, 64, 3>));
     PIGP_PRELOAD((k_gemm_s<32, 64, 3>));
-    PIGP_CUDA(cudaFuncSetAttribute(k_trsm_refine<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem(8)));
-    PIGP_CUDA(cudaFuncSetAttribute(k_trsm_refine<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem(16)));
-    PIGP_CUDA(cudaFuncSetAttribute(k_trsm_refine<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem(32)));
-    PIGP_CUDA(cudaFuncSetAttribute(k_trsm_refine<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem(64)));
-    PIGP_PRELOAD(k_trsm_refine<8>);
-    PIGP_PRELOAD(k_trsm_refine<16>);
-    PIGP_PRELOAD(k_trsm_refine<32>);
-    PIGP_PRELOAD(k_trsm_refine<64>);
+    PIGP_CUDA(cudaFuncSetAttribute(k_trsm_blk<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tb_smem(8)));
+    PIGP_CUDA(cudaFuncSetAttribute(k_trsm_blk<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tb_smem(16)));
+    PIGP_CUDA(cudaFuncSetAttribute(k_trsm_blk<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tb_smem(32)));
+    PIGP_PRELOAD(k_trsm_blk<8>);
+    PIGP_PRELOAD(k_trsm_blk<16>);
+    PIGP_PRELOAD(k_trsm_blk<32>);
     PIGP_TRY((gemm_attrs<128, 4>()));
     PIGP_TRY((gemm_attrs<64, 3>()));
     PIGP_CUDA(cudaFuncSetAttribute(k_potf2, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM));
     PIGP_PRELOAD(k_potf2);
+    PIGP_CUDA(cudaFuncSetAttribute(k_tile_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM));
+    PIGP_PRELOAD(k_tile_inv);
     PIGP_PRELOAD(k_place_diag);
     PIGP_PRELOAD(k_logdet_quad);
     PIGP_PRELOAD(k_trmv_lower_t);

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) k_push_diag(const double* invk, const dou
     const int r0 = blockIdx.x * 16;
     for (int e = threadIdx.x; e < 16 * 64; e += 256) {
         const int i = r0 + (e >> 6), j2 = (e & 63) * 2;
-        if (j2 <= i) {
+        if (j2 <= i && (j2 >> 5) == (i >> 5)) {  // the diagonal 32-blocks of the inverse: all that a peer's TRSM reads
             const double2 v = *reinterpret_cast<const double2*>(invk + i * 128 + j2);
             for (int p = 0; p < pd.n; ++p) *reinterpret_cast<double2*>(pd.invd[p] + i * 128 + j2) = v;
         }
@@ -377,7 +377,7 @@ int leaf(const Ctx& c, int k) {
     double* invk = s->invd + (int64_t)k * TILE * TILE;
     double* Akk = s->L + (int64_t)k * TILE * ld + (int64_t)k * TILE;
     const bool mine = (k % s->world == s->rank), multi = c.npeers > 0;
-    if (mine) PIGP_TRY(launch_potf2(Akk, ld, invk, s->info, k * TILE, PeerTiles{}, c.st));
+    if (mine) PIGP_TRY(launch_potf2(Akk, ld, invk, s->info, k * TILE, c.st));
     if (c.grad || multi) PIGP_CUDA(cudaEventRecord(s->ev_diag[k], c.st));  // mine: inv(L_kk) is ready; else: the chain has reached leaf k
     if (mine && multi) {
         // publish inv(L_kk) and diag(L_kk) from the publication stream while the chain goes on with this rank's own TRSM
@@ -426,14 +426,11 @@ int leaf(const Ctx& c, int k) {
         }
     }
     if (c.grad) {
-        // Y[j, k] = R[j, k] inv(L_kk)^T for own row tiles j < k; Y[k, k] = inv(L_kk)^T
+        // Y[j, k] = R[j, k] inv(L_kk)^T for own row tiles j < k; Y[k, k] = inv(L_kk)^T.  The factorisation only produced
+        // the diagonal 32-blocks of inv(L_kk); every rank completes the tile itself from its copy of L_kk, here, off the chain
         PIGP_CUDA(cudaStreamWaitEvent(c.sb, s->ev_diag[k], 0));
-        if (mine) {
-            ProfScope prof(PROF_MISC, c.sb);
-            k_place_diag_t<<<16, 256, 0, c.sb>>>(s->Y, ld, s->invd, k, 1);
-            count_launch();
-            PIGP_CUDA(cudaGetLastError());
-        }
+        if (!mine) PIGP_TRY(wait_one(c, s->f_diag(k), c.sb));
+        PIGP_TRY(launch_tile_inv(s->L, ld, s->invd, k, 1, 1, mine ? s->Y : nullptr, ld, c.sb));
         const int first = s->first_own(0), cnt = s->count_own(0, k);
         if (cnt > 0) {
             GemmDesc g{};
@@ -445,7 +442,6 @@ int leaf(const Ctx& c, int k) {
             g.C = Cb; g.ldc = ld;
             g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = k; g.k_gt0 = k;
             g.force_bn128 = 1;
-            if (!mine) PIGP_TRY(set_wait_one(c, g, s->f_diag(k), c.sb));
             PIGP_TRY(launch_gemm(g, c.sb));
         }
     }

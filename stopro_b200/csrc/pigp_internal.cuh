@@ -205,10 +205,11 @@ struct GemmDesc {
     unsigned long long* sig_flag[7];
 };
 int launch_gemm(const GemmDesc& g, cudaStream_t st);
-struct PeerTiles {  // peer addresses of the diagonal tile / its inverse, and the epoch flag published after they are stored
-    int n; double* a[7]; double* invd[7]; unsigned long long* flag[7]; unsigned long long val;
-};
-int launch_potf2(double* A, int64_t ld, double* invd, int32_t* info, int base, const PeerTiles& peers, cudaStream_t st);
+// factor one 128 x 128 diagonal tile in place; invd receives the four diagonal 32 x 32 blocks of inv(L) only
+int launch_potf2(double* A, int64_t ld, double* invd, int32_t* info, int base, cudaStream_t st);
+// complete the inverse tiles c = first + i * stride (i < count) from L_cc and their diagonal blocks; Y != nullptr: also
+// write inv(L_cc)^T into the diagonal tile c of Y (row stride ldy)
+int launch_tile_inv(const double* L, int64_t ld, double* invd, int first, int stride, int count, double* Y, int64_t ldy, cudaStream_t st);
 int potrf_lower(double* A, int64_t ld, int64_t n, int64_t m_extra, double* invd, int32_t* info, cudaStream_t st);
 int potri_lower(const double* L, int64_t ld, int64_t n, const double* invd, double* W, double* X, cudaStream_t st);
 // out[0] = sum_{i<n} log A[i*ld+i]; out[1] = sum_{j<n} v[j]^2  (v = row `vrow` of A)

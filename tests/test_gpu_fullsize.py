@@ -35,7 +35,9 @@ def test_nll_is_quadratic_in_y(problem):
     cfg, gp, solver, th, nll, _ = problem
     y, eps = cfg["delta_y"], cfg["eps"]
     f = [solver.nll_grad_host(th, c * y, eps, want_grad=False)[0] for c in (0.0, 1.0, 2.0)]
-    assert f[1] == pytest.approx(nll, rel=1e-13)
+    # the NLL-only evaluation takes the panel schedule, the NLL+gradient one the plain recursion: same factorisation in a
+    # different summation order, so they agree to rounding amplified by cond(K) (~1e-10 here), not bitwise
+    assert f[1] == pytest.approx(nll, rel=1e-9)
     quad = 2.0 * (f[1] - f[0])                      # y^T K^-1 y
     assert quad > 0.0
     assert abs(f[2] - 4.0 * f[1] + 3.0 * f[0]) <= 1e-10 * max(abs(f[1]), abs(quad))

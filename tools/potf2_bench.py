@@ -37,7 +37,7 @@ torch.cuda.synchronize()
 _lib.check(lib.pigp_debug_potf2_stamps(None))
 t = st.cpu().tolist()
 names = ["load", "potrf32[0]", "panel[0]", "trail[0]+potrf32[1]", "panel[1]", "trail[1]+potrf32[2]", "panel[2]",
-         "trail[2]+potrf32[3]", "(loop exit)", "store L", "inverse", "store invd"]
+         "trail[2]+potrf32[3]", "(loop exit)", "store L", "store diagonal inverse blocks", "(end)"]
 for i, nme in enumerate(names):
     print(f"  {nme:22s} {t[i + 1] - t[i]:8d} cycles")
 print(f"  total                  {t[12] - t[0]:8d} cycles")
