@@ -15,6 +15,7 @@
 // * Host drivers: recursive right-looking Cholesky (all flops in k_gemm), TRTRI + LAUUM for K^-1.
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "pigp_internal.cuh"
 
@@ -43,6 +44,21 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+// Shared-memory mbarriers (producer / consumer hand-off between warps of a CTA)
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("{\n .reg .b64 t;\n mbarrier.arrive.shared::cta.b64 t, [%0];\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
 }
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -280,6 +296,9 @@ __global__ void __launch_bounds__(BN_ * 2) k_gemm_s(GemmDesc g) {
     if (kt_end <= kt_begin && g.beta == 1.0) return;
     wait_flags(g, tid);
 
+    // C -= A B^T (the trailing updates on the latency-bound chain): the accumulators start from -C, fetched while the first
+    // operand tiles are still in flight, instead of a read-modify-write of C after the last MMA
+    const bool fold = (g.alpha == -1.0 && g.beta == 1.0);
     double acc[MI][4][2];
 #pragma unroll
     for (int i = 0; i < MI; ++i)
@@ -294,6 +313,19 @@ __global__ void __launch_bounds__(BN_ * 2) k_gemm_s(GemmDesc g) {
             load_operand<true, BN_, THREADS>(smem + s * STG + OPA, g.B, g.ldb, n0, (int64_t)(kt_begin + s) * BK, tid);
         }
         cp_async_commit();
+    }
+    if (fold) {
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi) {
+            const double* crow = g.C + (m0 + wm * (BM_ / 2) + 8 * mi + gid) * g.ldc + n0 + wn * 32;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const double2 a0 = *reinterpret_cast<const double2*>(crow + 16 * q + 2 * tig);
+                const double2 a1 = *reinterpret_cast<const double2*>(crow + 16 * q + 2 * tig + 8);
+                acc[mi][2 * q][0] = -a0.x; acc[mi][2 * q][1] = -a0.y;
+                acc[mi][2 * q + 1][0] = -a1.x; acc[mi][2 * q + 1][1] = -a1.y;
+            }
+        }
     }
     for (int it = 0; it < nk; ++it) {
         cp_async_wait<STAGES_ - 2>();
@@ -339,7 +371,7 @@ __global__ void __launch_bounds__(BN_ * 2) k_gemm_s(GemmDesc g) {
             double2* p1 = reinterpret_cast<double2*>(crow + c1);
             double2 o0 = make_double2(g.alpha * acc[mi][2 * q][0], g.alpha * acc[mi][2 * q][1]);
             double2 o1 = make_double2(g.alpha * acc[mi][2 * q + 1][0], g.alpha * acc[mi][2 * q + 1][1]);
-            if (g.beta != 0.0) {
+            if (g.beta != 0.0 && !fold) {
                 const double2 a0 = *p0, a1 = *p1;
                 o0.x = fma(g.beta, a0.x, o0.x); o0.y = fma(g.beta, a0.y, o0.y);
                 o1.x = fma(g.beta, a1.x, o1.x); o1.y = fma(g.beta, a1.y, o1.y);
@@ -450,19 +482,34 @@ __global__ void __launch_bounds__(256) k_trsm_blk(GemmDesc g) {
     const int64_t m0 = (int64_t)(tm / SUB) * g.m_ts * BM + (tm % SUB) * TR_BM;
     wait_flags(g, tid);
     // one group of asynchronous copies per column block: what step jb needs (its 32 columns of the slab, row jb of the
-    // blocks of Lkk, W_jb) arrives while steps 0 .. jb - 1 compute
+    // blocks of Lkk, W_jb) arrives while steps 0 .. jb - 1 compute.  Thread (lr, lch) copies 16 bytes of rows lr and
+    // lr + 16 of every 32 x 32 block: all offsets are compile-time multiples of the row strides (the issue of these ~30
+    // copies per thread was 45 % of the kernel with per-copy index arithmetic).
+    {
+        const int lr = tid >> 4, lch = (tid & 15) * 2;
+        const double* srcA = g.A + (m0 + lr) * g.lda + lch;
+        const double* srcL = g.Lkk + (int64_t)lr * g.ldl + lch;
+        const double* srcW = g.B + (int64_t)lr * g.ldb + lch;
+        double* dstS = S + lr * TB_SLD + lch;
+        double* dstL = Ls + lr * TB_LD + lch;
+        double* dstW = Ws + lr * TB_LD + lch;
+        const int64_t l16 = 16 * (int64_t)g.ldl, w16 = 16 * (int64_t)g.ldb;
 #pragma unroll
-    for (int jb = 0; jb < 4; ++jb) {
-        for (int c = tid; c < TR_BM * 16; c += 256) {
-            const int r = c >> 4, ch = (c & 15) * 2;
-            cp_async16(S + r * TB_SLD + 32 * jb + ch, g.A + (m0 + r) * g.lda + 32 * jb + ch);
+        for (int jb = 0; jb < 4; ++jb) {
+            if (lr < TR_BM) cp_async16(dstS + 32 * jb, srcA + 32 * jb);
+            if (TR_BM > 16) cp_async16(dstS + 16 * TB_SLD + 32 * jb, srcA + 16 * g.lda + 32 * jb);
+            const double* rowL = srcL + 2 * jb * l16;
+#pragma unroll
+            for (int ib = 0; ib <= jb; ++ib) {
+                double* d = dstL + (jb * (jb + 1) / 2 + ib) * 32 * TB_LD;
+                cp_async16(d, rowL + 32 * ib);
+                cp_async16(d + 16 * TB_LD, rowL + l16 + 32 * ib);
+            }
+            const double* rowW = srcW + 2 * jb * w16 + 32 * jb;
+            cp_async16(dstW + jb * 32 * TB_LD, rowW);
+            cp_async16(dstW + jb * 32 * TB_LD + 16 * TB_LD, rowW + w16);
+            cp_async_commit();
         }
-        for (int c = tid; c < (jb + 2) * 512; c += 256) {
-            const int ib = c >> 9, r = (c >> 4) & 31, ch = (c & 15) * 2;
-            if (ib <= jb) cp_async16(Ls + ((jb * (jb + 1) / 2 + ib) * 32 + r) * TB_LD + ch, g.Lkk + (int64_t)(32 * jb + r) * g.ldl + 32 * ib + ch);
-            else cp_async16(Ws + (jb * 32 + r) * TB_LD + ch, g.B + (int64_t)(32 * jb + r) * g.ldb + 32 * jb + ch);
-        }
-        cp_async_commit();
     }
     const bool active = warp * TPW < N_TILES;
     const int rt = (warp * TPW) >> 2, ct0 = (warp * TPW) & 3;  // this warp's tiles: row tile rt, column tiles ct0 .. ct0 + TPW
@@ -748,55 +795,43 @@ __device__ __forceinline__ double rsqrt_pivot(double d) {
 // Warp-level Cholesky of the 32 x 32 block at D (shared memory, row stride ld), and its inverse by a second warp.
 // Factor (warp_factor32): lane i owns row i of the block in registers.  The 32 columns are eliminated in 16 pairs: for
 // the 2 x 2 pivot block [d0 b; b d1] the two reciprocal roots rsqrt(d0) and rsqrt(d0 d1 - b^2) are independent, so the
-// pivot -> rsqrt -> scale -> pivot dependency chain has 16 links instead of 32.  Per pair every lane publishes
-// (L[i][j], L[i][j+1], its own future pivot S[i][i], S[i][j+2]) in shared memory -- one exchange -- from which all lanes
-// rebuild the next pivot block redundantly, ahead of the rank-2 update of the rows, so that the chain (~13 dependent FP64
-// operations of ~20 cycles) runs underneath the update.  L overwrites the lower triangle of D (zeros above).
+// pivot -> rsqrt -> scale -> pivot dependency chain has 16 links instead of 32.  Every lane rebuilds the next pivot block
+// redundantly from seven shuffled numbers (L[i][j], L[i][j+1], the future pivots S[i][i] of rows j+2, j+3 and
+// S[j+3][j+2]) ahead of the rank-2 update of the rows, so that the chain (~10 dependent FP64 operations of ~25 cycles plus
+// the MUFU seed) runs underneath the update.  L overwrites the lower triangle of D (zeros above).
 // Inverse (warp_inverse32): lane c solves column c of W = inv(L) right-looking (w_j = r_j / L_jj; r_m -= L[m][j] w_j),
 // two columns of L at a time as soon as the factoring warp has released them (one mbarrier per column pair), with
 // the factor's entries coming from broadcast loads.  W goes to Winv (row stride SLD, zeros above the diagonal).
-struct __align__(16) PairXch { double l0, l1, piv, sub; };
 
-// Shared-memory mbarriers hand the finished column pairs from the factoring warp to the inverting warp: arrive (release)
-// does not block the producer, try_wait (acquire) orders the consumer's loads behind the producer's stores.
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("{\n .reg .b64 t;\n mbarrier.arrive.shared::cta.b64 t, [%0];\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
-    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
-    unsigned ok;
-    do {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    } while (!ok);
-}
+// (The finished column pairs go from the factoring warp to the inverting warp through mbarriers: arrive (release) does
+// not block the producer, try_wait (acquire) orders the consumer's loads behind the producer's stores.)
 
-// Scalars of the 2 x 2 pivot block [d0 b; b d1]: 1 / l00, l10 and 1 / l11 of its Cholesky factor.  Branch-free (a
-// non-positive pivot is recorded in `fail`, 1-based column inside the block, first one wins; NaNs propagate).
-struct PairScal { double r0, l10, r1; };
+// Scalars of the 2 x 2 pivot block [d0 b; b d1]: r0 = 1 / l00, l10, l00 and rdet = 1 / sqrt(d0 d1 - b^2), from which
+// 1 / l11 = rdet l00.  Branch-free (a non-positive pivot is recorded in `fail`, 1-based column inside the block, first
+// one wins; NaNs propagate).  d0 d1 is formed (with its rounding error) while b is still on its way, so the determinant
+// costs two dependent operations after b.
+struct PairScal { double r0, l10, l00, rdet; };
 
 __device__ __forceinline__ PairScal pivot_block(double d0, double d1, double b, int col, int& fail) {
-    const double b2 = b * b;
-    const double det = fma(d0, d1, -b2) - fma(b, b, -b2);  // d0 d1 - b^2 with the rounding of b^2 compensated
+    const double dd = d0 * d1, dde = fma(d0, d1, -dd);
+    const double det = fma(-b, b, dd) + dde;
     fail = (fail == 0 && !(d0 > 0.0)) ? col + 1 : fail;
     fail = (fail == 0 && !(det > 0.0)) ? col + 2 : fail;
     const double r0 = rsqrt_pivot(d0), rdet = rsqrt_pivot(det);
     PairScal sc;
     sc.r0 = r0;
     sc.l10 = b * r0;
-    sc.r1 = rdet * (d0 * r0);  // sqrt(d0 / det) = 1 / sqrt(d1 - b^2 / d0)
+    sc.l00 = d0 * r0;
+    sc.rdet = rdet;
     return sc;
 }
 
 // (template recursion instead of #pragma unroll: the rows must stay in registers, and the unroller gives up on the long
 // inner loops of the first pairs, which would put the array into local memory)
 template <int K>
-__device__ __forceinline__ void pair_update(double (&a)[32], const PairXch* nxt, double l0, double l1) {
+__device__ __forceinline__ void pair_update(double (&a)[32], const double2* nxt, double l0, double l1) {
     if constexpr (K < 32) {
-        const double2 c = *reinterpret_cast<const double2*>(&nxt[K].l0);  // (L[K][j], L[K][j+1]): broadcast load
+        const double2 c = nxt[K];  // (L[K][j], L[K][j+1]): broadcast load
         a[K] = fma(-l1, c.y, fma(-l0, c.x, a[K]));
         pair_update<K + 1>(a, nxt, l0, l1);
     }
@@ -804,31 +839,32 @@ __device__ __forceinline__ void pair_update(double (&a)[32], const PairXch* nxt,
 
 // One pair of columns.  Every lane applies the same formulas: for the block's own rows they reproduce l00, l10 and l11
 // (lane J holds d0 in a[J]; lane J + 1 holds b and d1), rows above the block compute garbage that nobody reads and that
-// is masked when the columns are stored -- straight-line code.
+// is masked when the columns are stored -- straight-line code.  The new columns go to shared memory for the rank-2 update
+// (broadcast loads) and for the inverting warp; the seven numbers the next pivot block depends on travel by shuffles,
+// so that the dependency chain per pair is shuffle -> 4 operations -> rsqrt (MUFU + 4) -> 2 operations.
 template <int J>
-__device__ __forceinline__ void pair_step(double (&a)[32], double& piv, const PairScal sc, int& fail, PairXch* xch, double* D,
+__device__ __forceinline__ void pair_step(double (&a)[32], double& piv, const PairScal sc, int& fail, double2* xch, double* D,
                                           int ld, double* rdiag, unsigned long long* bars, int lane) {
     if constexpr (J < 32) {
         const double l0 = a[J] * sc.r0;
-        const double l1 = fma(-l0, sc.l10, a[J + 1]) * sc.r1;
+        const double l1 = (fma(-l0, sc.l10, a[J + 1]) * sc.l00) * sc.rdet;
         piv = fma(-l1, l1, fma(-l0, l0, piv));
-        PairXch* nxt = xch + (((J >> 1) + 1) & 1) * 32;
-        {
-            PairXch e;
-            e.l0 = l0; e.l1 = l1; e.piv = piv;
-            if constexpr (J + 2 < 32) e.sub = a[J + 2]; else e.sub = 0.0;
-            nxt[lane] = e;
-        }
-        // columns J, J + 1 of L are final: back to shared memory at once (frees their registers, feeds the inverting warp)
-        *reinterpret_cast<double2*>(D + lane * ld + J) = make_double2(lane >= J ? l0 : 0.0, lane > J ? l1 : 0.0);
-        if (lane == 0) *reinterpret_cast<double2*>(rdiag + J) = make_double2(sc.r0, sc.r1);
-        mbar_arrive(bars + (J >> 1));  // all 32 lanes: each releases its own row's stores
-        __syncwarp();
         PairScal nsc{};
         if constexpr (J + 3 < 32) {
-            const PairXch p2 = nxt[J + 2], p3 = nxt[J + 3];
-            nsc = pivot_block(p2.piv, p3.piv, fma(-p3.l1, p2.l1, fma(-p3.l0, p2.l0, p3.sub)), J + 2, fail);
+            constexpr unsigned FULL = 0xffffffffu;
+            const double p2l0 = __shfl_sync(FULL, l0, J + 2), p3l0 = __shfl_sync(FULL, l0, J + 3);
+            const double p3sub = __shfl_sync(FULL, a[J + 2], J + 3);
+            const double p2l1 = __shfl_sync(FULL, l1, J + 2), p3l1 = __shfl_sync(FULL, l1, J + 3);
+            const double d0 = __shfl_sync(FULL, piv, J + 2), d1 = __shfl_sync(FULL, piv, J + 3);
+            nsc = pivot_block(d0, d1, fma(-p3l1, p2l1, fma(-p3l0, p2l0, p3sub)), J + 2, fail);
         }
+        double2* nxt = xch + (((J >> 1) + 1) & 1) * 32;
+        nxt[lane] = make_double2(l0, l1);
+        // columns J, J + 1 of L are final: back to shared memory at once (frees their registers, feeds the inverting warp)
+        *reinterpret_cast<double2*>(D + lane * ld + J) = make_double2(lane >= J ? l0 : 0.0, lane > J ? l1 : 0.0);
+        if (lane == 0) *reinterpret_cast<double2*>(rdiag + J) = make_double2(sc.r0, sc.rdet * sc.l00);
+        mbar_arrive(bars + (J >> 1));  // all 32 lanes: each releases its own row's stores
+        __syncwarp();
         pair_update<J + 2>(a, nxt, l0, l1);
         pair_step<J + 2>(a, piv, nsc, fail, xch, D, ld, rdiag, bars, lane);
     }
@@ -836,19 +872,14 @@ __device__ __forceinline__ void pair_step(double (&a)[32], double& piv, const Pa
 
 __device__ __noinline__ void warp_factor32(double* D, int ld, double* xch_sm, double* rdiag, unsigned long long* bars,
                                               int32_t* info, int base, int lane) {
-    PairXch* xch = reinterpret_cast<PairXch*>(xch_sm);  // 2 x 32 entries, double-buffered
+    double2* xch = reinterpret_cast<double2*>(xch_sm);  // 2 x 32 entries, double-buffered
     double a[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? D[lane * ld + c] : 0.0;
     double piv = D[lane * ld + lane];
-    {
-        PairXch e;
-        e.l0 = 0.0; e.l1 = 0.0; e.piv = piv; e.sub = a[0];  // lane 1: S[1][0]
-        xch[lane] = e;
-    }
-    __syncwarp();
     int fail = 0;
-    const PairScal sc = pivot_block(xch[0].piv, xch[1].piv, xch[1].sub, 0, fail);
+    constexpr unsigned FULL = 0xffffffffu;
+    const PairScal sc = pivot_block(__shfl_sync(FULL, piv, 0), __shfl_sync(FULL, piv, 1), __shfl_sync(FULL, a[0], 1), 0, fail);
     pair_step<0>(a, piv, sc, fail, xch, D, ld, rdiag, bars, lane);
     if (lane == 0 && info && fail) atomicCAS(info, 0, base + fail);
     POTF2_STAMP(13);
@@ -902,23 +933,20 @@ __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double*
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     POTF2_STAMP(0);
     // lower 32 x 32 blocks of the tile -> shared memory (16-byte asynchronous copies, all in flight at once).  The strictly
-    // upper blocks are never read, except (0,1) and (2,3) by the products of the inverse: those are zeroed; the upper
-    // triangles of the diagonal blocks are zeroed by the factoring warp when it writes the columns back.
+    // upper blocks are never read; the upper triangles of the diagonal blocks are zeroed by the factoring warp when it
+    // writes the columns back.  (Bulk copies of the 256-byte block rows through the TMA engine were measured slower here
+    // and in k_trsm_blk: 4.6k vs 3.0k cycles for this tile.)
 #pragma unroll 8
     for (int c = tid; c < PT * PT / 2; c += 256) {
         const int i = c >> 6, j2 = (c & 63) * 2;
         if ((j2 >> 5) <= (i >> 5)) cp_async16(sm + i * PLD + j2, A + (int64_t)i * ld + j2);
     }
     cp_async_commit();
-    for (int e = tid; e < 2 * 32 * 32; e += 256) {
-        const int half = e >> 10, i = (e >> 5) & 31, j = e & 31;
-        sm[(64 * half + i) * PLD + 64 * half + 32 + j] = 0.0;
-    }
     cp_async_wait<0>();
     __syncthreads();
     POTF2_STAMP(1);
     // kb = -1: factor block 0; kb >= 0: panel kb, then the trailing update of which warp 0 takes the next diagonal block
-    // (strips 0-3 of column group 0) and factors it at once while warps 1-7 update the rest; warp 1 then inverts the block
+    // (strips 0-3 of column group 0) and factors it at once while warps 2-7 update the rest and warp 1 inverts the block
     // behind the factoring warp.  (One call site of the factor / inverse: their straight-line code is ~50 KB, a second copy
     // would thrash the instruction cache -- the loop start is opaque so that the first iteration is not peeled.)
     const int kb_first = (ld < 0) ? 0 : -1;
@@ -954,7 +982,7 @@ __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double*
                 for (int st = 4; st < n_strips; ++st) {
                     const int n_groups = st / 4 + 1;
                     for (int cg = 0; cg < n_groups; ++cg, ++task) {
-                        if (task % 7 != warp - 1) continue;
+                        if (warp < 2 || task % 6 != warp - 2) continue;  // warp 1 only inverts: it must keep up with warp 0
                         const int r0 = r_lo + st * 8, c0 = r_lo + cg * 32;
                         const int n_tiles = min(4, (r0 - c0) / 8 + 1);  // tiles at or left of the diagonal tile
                         strip_mma<false, 32>(sm + r0 * PLD + c0, PLD, sm + r0 * PLD + o, PLD, sm + c0 * PLD + o, PLD, -1.0, true,
@@ -968,17 +996,14 @@ __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double*
         POTF2_STAMP(4 + 2 * kb);
     }
     POTF2_STAMP(9);
-    // L -> global: the lower 32-blocks (16-byte stores; zeros above the diagonal inside the diagonal blocks).  The strictly
-    // upper blocks of the tile keep their input values: no kernel reads them, and a single SM's store path is ~32 B/clk
-#pragma unroll 8
-    for (int c = tid; c < PT * PT / 2; c += 256) {
-        const int i = c >> 6, j2 = (c & 63) * 2;
-        if ((j2 >> 5) <= (i >> 5)) {
-            double2 v = *reinterpret_cast<const double2*>(sm + i * PLD + j2);
-            if (j2 > i) v.x = 0.0;
-            if (j2 + 1 > i) v.y = 0.0;
-            *reinterpret_cast<double2*>(A + (int64_t)i * ld + j2) = v;
-        }
+    // L -> global: the ten lower 32-blocks (16-byte stores; the diagonal blocks carry their zeros above the diagonal from
+    // the factoring warp).  The strictly upper blocks of the tile keep their input values: no kernel reads them.
+#pragma unroll 4
+    for (int q = tid; q < 10 * 512; q += 256) {
+        const int blk = q >> 9, r = (q >> 4) & 31, ch = (q & 15) * 2;
+        const int rb = blk < 1 ? 0 : blk < 3 ? 1 : blk < 6 ? 2 : 3, cb = blk - rb * (rb + 1) / 2;
+        const int i = 32 * rb + r, j2 = 32 * cb + ch;
+        *reinterpret_cast<double2*>(A + (int64_t)i * ld + j2) = *reinterpret_cast<const double2*>(sm + i * PLD + j2);
     }
     POTF2_STAMP(10);
     // the four diagonal blocks of inv(L) -> invd: all that the block TRSM of the panel reads.  The rest of the inverse tile
@@ -1145,9 +1170,67 @@ static int chol_rec(double* A, int64_t ld, int64_t n, int64_t m_below, double* i
         g.B = A + n1 * ld; g.ldb = ld; g.b_kcontig = 1;
         g.C = A + n1 * ld + n1; g.ldc = ld;
         g.lower_only = 1;
+        g.gen = 1; g.m_ts = 1;  // tile-indexed form (row tile 0 = column tile 0): eligible for the small-tile kernels
         PIGP_TRY(launch_gemm(g, st));
     }
     return chol_rec(A + n1 * ld + n1, ld, n2, m_below, invd + (n1 / TILE) * TILE * TILE, info, base + (int)n1, st);
+}
+
+// Panel schedule with look-ahead for the stand-alone factorisation (the solver has its own, pigp_dist.cu): coarse panels
+// of W tile columns, the recursion inside a panel (and its TRSM of all rows below) on the caller's stream, the panel's
+// update of the columns to its right on a bulk stream -- the next panel's columns first, the chain waits only for those.
+struct PanelStreams { cudaStream_t bulk = nullptr; std::vector<cudaEvent_t> pan, next; cudaEvent_t done = nullptr; };
+static PanelStreams g_panel_streams[64];
+
+static int panel_update_dense(double* A, int64_t ld, int64_t rows, int64_t j0, int64_t j1, int64_t c0, int64_t c1, cudaStream_t st) {
+    // C[c0.., [c0, c1)] -= L[c0.., [j0, j1)] L[[c0, c1), [j0, j1)]^T for all `rows` rows from c0 down (lower part)
+    if (c1 <= c0) return PIGP_OK;
+    GemmDesc g{};
+    g.M = (int)(rows - c0); g.N = (int)(c1 - c0); g.K = (int)(j1 - j0);
+    g.alpha = -1.0; g.beta = 1.0;
+    g.A = A + c0 * ld + j0; g.lda = ld; g.a_kcontig = 1;
+    g.B = A + c0 * ld + j0; g.ldb = ld; g.b_kcontig = 1;
+    g.C = A + c0 * ld + c0; g.ldc = ld;
+    g.lower_only = 1;
+    g.gen = 1; g.m_ts = 1;
+    return launch_gemm(g, st);
+}
+
+static int chol_panels(double* A, int64_t ld, int64_t n, int64_t m_extra, double* invd, int32_t* info, int W, cudaStream_t st) {
+    int dev = 0;
+    PIGP_CUDA(cudaGetDevice(&dev));
+    PanelStreams& ps = g_panel_streams[dev & 63];
+    const int T = (int)(n / TILE), n_pan = (T + W - 1) / W;
+    if (!ps.bulk) {
+        PIGP_CUDA(cudaStreamCreateWithFlags(&ps.bulk, cudaStreamNonBlocking));
+        PIGP_CUDA(cudaEventCreateWithFlags(&ps.done, cudaEventDisableTiming));
+    }
+    while ((int)ps.pan.size() < n_pan) {
+        cudaEvent_t a = nullptr, b = nullptr;
+        PIGP_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        PIGP_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        ps.pan.push_back(a);
+        ps.next.push_back(b);
+    }
+    const int64_t rows = n + m_extra, w = (int64_t)W * TILE;
+    // the bulk stream starts behind everything already queued on the caller's stream
+    PIGP_CUDA(cudaEventRecord(ps.done, st));
+    PIGP_CUDA(cudaStreamWaitEvent(ps.bulk, ps.done, 0));
+    for (int64_t j0 = 0, p = 0; j0 < n; j0 += w, ++p) {
+        const int64_t j1 = std::min(j0 + w, n);
+        PIGP_TRY(chol_rec(A + j0 * ld + j0, ld, j1 - j0, rows - j1, invd + (j0 / TILE) * TILE * TILE, info, (int)j0, st));
+        if (j1 >= rows) break;
+        PIGP_CUDA(cudaEventRecord(ps.pan[p], st));
+        PIGP_CUDA(cudaStreamWaitEvent(ps.bulk, ps.pan[p], 0));
+        const int64_t jn = std::min(j1 + w, n);
+        if (j1 < n) PIGP_TRY(panel_update_dense(A, ld, rows, j0, j1, j1, jn, ps.bulk));
+        PIGP_CUDA(cudaEventRecord(ps.next[p], ps.bulk));
+        if (jn < n) PIGP_TRY(panel_update_dense(A, ld, rows, j0, j1, jn, n, ps.bulk));
+        PIGP_CUDA(cudaStreamWaitEvent(st, ps.next[p], 0));
+    }
+    PIGP_CUDA(cudaEventRecord(ps.done, ps.bulk));
+    PIGP_CUDA(cudaStreamWaitEvent(st, ps.done, 0));
+    return PIGP_OK;
 }
 
 int potrf_lower(double* A, int64_t ld, int64_t n, int64_t m_extra, double* invd, int32_t* info, cudaStream_t st) {
@@ -1155,7 +1238,10 @@ int potrf_lower(double* A, int64_t ld, int64_t n, int64_t m_extra, double* invd,
         set_error("pigp potrf: n and m_extra must be multiples of 128 and ld even");
         return PIGP_EINVAL;
     }
-    PIGP_TRY(chol_rec(A, ld, n, m_extra, invd, info, 0, st));
+    const int T = (int)(n / TILE);
+    const int W = T < 12 ? 0 : T < 64 ? 2 : T < 128 ? 4 : 8;  // same rule as the solver's NLL-only evaluation
+    if (W > 0) PIGP_TRY(chol_panels(A, ld, n, m_extra, invd, info, W, st));
+    else PIGP_TRY(chol_rec(A, ld, n, m_extra, invd, info, 0, st));
     // the factorisation leaves the diagonal 32-blocks of the inverse tiles; callers of this entry point get complete tiles
     return launch_tile_inv(A, ld, invd, 0, 1, (int)(n / TILE), nullptr, 0, st);
 }

@@ -514,12 +514,14 @@ int rec(const Ctx& c, int c0, int nt) {
 // Width: PIGP_LOOKAHEAD / pigp_set_lookahead(W >= 0) fix it (0 = plain recursion); unset (or a negative W) = automatic:
 // a single-rank NLL-only evaluation has no L^-T work on the side stream to fill the bubbles of the potf2 -> TRSM chain,
 // and the panel schedule measured 18 % / 13 % / 5 % faster there at N = 5018 / 10570 / 20000 (profiles/r02_lookahead.txt);
-// with the gradient requested, or sharded, the plain recursion is within 3 % and stays the default.
+// with the gradient requested the L^-T products fill most of those bubbles (a few per cent gain at mid sizes only), and
+// sharded runs keep the plain recursion.
 static int g_lookahead = -2;  // -2: read PIGP_LOOKAHEAD once; -1: automatic; >= 0: fixed
 static int lookahead_width(const pigp_dsolver* s, bool grad) {
     if (g_lookahead == -2) { const char* e = getenv("PIGP_LOOKAHEAD"); g_lookahead = e ? std::max(0, atoi(e)) : -1; }
     if (g_lookahead >= 0) return g_lookahead;
-    if (grad || s->world != 1 || s->T < 12) return 0;
+    if (s->world != 1 || s->T < 12) return 0;
+    if (grad) return (s->T >= 16 && s->T < 32) ? 2 : (s->T >= 32 && s->T < 96) ? 4 : 0;  // -6 % at N = 2640, -4 % at 5018
     return s->T < 64 ? 2 : s->T < 128 ? 4 : 8;
 }
 
