@@ -253,7 +253,7 @@ int pigp_set_side_stream(int on);
 /* Panel schedule of the factorisation: tiles = 0 is the plain recursion; tiles = W > 0 factors coarse panels of W tile
  * columns on the chain stream and applies each panel to the rest of the matrix on a bulk stream, one panel ahead (the big
  * trailing updates leave the N/128-step dependency chain); tiles < 0 = automatic, which is the default when PIGP_LOOKAHEAD
- * is unset: panels (W = 2 / 4 / 8 by size) for single-GPU NLL-only evaluations of 12 tiles or more -- they have no L^-T
+ * is unset: panels (W = 2 / 4 / 16 by size) for single-GPU NLL-only evaluations of 12 tiles or more -- they have no L^-T
  * work to fill the chain's bubbles -- and the plain recursion otherwise.  Process-global. */
 int pigp_set_lookahead(int tiles);
 int pigp_profile_start(void);

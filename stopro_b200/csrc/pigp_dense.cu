@@ -945,74 +945,77 @@ __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double*
     cp_async_wait<0>();
     __syncthreads();
     POTF2_STAMP(1);
-    // kb = -1: factor block 0; kb >= 0: panel kb, then the trailing update of which warp 0 takes the next diagonal block
-    // (strips 0-3 of column group 0) and factors it at once while warps 2-7 update the rest and warp 1 inverts the block
-    // behind the factoring warp.  (One call site of the factor / inverse: their straight-line code is ~50 KB, a second copy
-    // would thrash the instruction cache -- the loop start is opaque so that the first iteration is not peeled.)
+    // kb = -1: factor block 0.  kb >= 0: warps 0-3 solve the first four 8-row strips of panel kb (L_ik = A_ik inv(L_kk)^T, in
+    // place) and update the next diagonal block with them -- two strip products, alone on the SM's FP64 tensor pipe -- after
+    // which warp 0 factors that block and warp 1 inverts it behind warp 0.  Underneath, warps 2, 3, 5, 6, 7 solve the rest of
+    // the panel, apply the trailing update to everything but the diagonal block and store what has become final (warp 4
+    // shares warp 0's scheduler and FP64 pipe and stays idle: the factoring warp's DFMA chain is the critical path).
+    // (One call site of the factor / inverse: their straight-line code is ~50 KB, a second copy would thrash the
+    // instruction cache -- the loop start is opaque so that the first iteration is not peeled.)
     const int kb_first = (ld < 0) ? 0 : -1;
+    const int bg = warp < 4 ? warp - 2 : warp - 3;  // background warps 2, 3, 5, 6, 7 -> 0 .. 4
 #pragma unroll 1
     for (int kb = kb_first; kb < 3; ++kb) {
         const int o = 32 * kb;
         const int r_lo = o + 32;
         const int n_strips = (PT - r_lo) / 8;
+        double* Dblk = sm + r_lo * PLD + r_lo;
+        const double* invk = scratch + kb * 32 * SLD;
         if (kb >= 0) {
-            // panel: rows below the block, L_ik = A_ik inv(L_kk)^T, in place (a strip is read entirely before it is written)
-            const double* invk = scratch + kb * 32 * SLD;
-            for (int st = warp; st < n_strips; st += 8) {
-                double* X = sm + (r_lo + st * 8) * PLD + o;
+            if (warp < 4) {
+                double* X = sm + (r_lo + warp * 8) * PLD + o;
                 strip_mma<false, 32>(X, PLD, X, PLD, invk, SLD, 1.0, false, 4, lane);
+                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                strip_mma<false, 32>(sm + (r_lo + warp * 8) * PLD + r_lo, PLD, X, PLD, sm + r_lo * PLD + o, PLD, -1.0, true, warp + 1, lane);
             }
             __syncthreads();
         }
         POTF2_STAMP(3 + 2 * kb);
-        double* Dblk = sm + r_lo * PLD + r_lo;
-        if (kb >= 0 && warp < 4) {
-            // the next diagonal block first: its four 8-row strips go to warps 0-3, which meet at a named barrier
-            const int st = warp;
-            strip_mma<false, 32>(sm + (r_lo + st * 8) * PLD + r_lo, PLD, sm + (r_lo + st * 8) * PLD + o, PLD, sm + r_lo * PLD + o, PLD,
-                                 -1.0, true, st + 1, lane);
-            asm volatile("bar.sync 1, 128;\n" ::: "memory");
-        }
         if (warp == 0) {
             warp_factor32(Dblk, PLD, xch, rdiag, bars, info, base + r_lo, lane);
-        } else {
-            if (kb >= 0) {
-                // trailing update (lower): tasks = (8-row strip, 32-column group at or left of it)
-                int task = 0;
-                for (int st = 4; st < n_strips; ++st) {
-                    const int n_groups = st / 4 + 1;
-                    for (int cg = 0; cg < n_groups; ++cg, ++task) {
-                        if (warp < 2 || task % 6 != warp - 2) continue;  // warp 1 only inverts: it must keep up with warp 0
-                        const int r0 = r_lo + st * 8, c0 = r_lo + cg * 32;
-                        const int n_tiles = min(4, (r0 - c0) / 8 + 1);  // tiles at or left of the diagonal tile
-                        strip_mma<false, 32>(sm + r0 * PLD + c0, PLD, sm + r0 * PLD + o, PLD, sm + c0 * PLD + o, PLD, -1.0, true,
-                                             n_tiles, lane);
-                    }
+        } else if (warp == 1) {
+            warp_inverse32(Dblk, PLD, scratch + (kb + 1) * 32 * SLD, rdiag, bars, (kb + 1) & 1, lane);
+        } else if (kb >= 0 && warp != 4) {
+            for (int st = 4 + bg; st < n_strips; st += 5) {
+                double* X = sm + (r_lo + st * 8) * PLD + o;
+                strip_mma<false, 32>(X, PLD, X, PLD, invk, SLD, 1.0, false, 4, lane);
+            }
+            asm volatile("bar.sync 2, 160;\n" ::: "memory");  // every strip of panel kb is final
+            // trailing update (lower): tasks = (8-row strip below the diagonal block, 32-column group at or left of it)
+            int task = 0;
+            for (int st = 4; st < n_strips; ++st) {
+                const int n_groups = st / 4 + 1;
+                for (int cg = 0; cg < n_groups; ++cg, ++task) {
+                    if (task % 5 != bg) continue;
+                    const int r0 = r_lo + st * 8, c0 = r_lo + cg * 32;
+                    const int n_tiles = min(4, (r0 - c0) / 8 + 1);  // tiles at or left of the diagonal tile
+                    strip_mma<false, 32>(sm + r0 * PLD + c0, PLD, sm + r0 * PLD + o, PLD, sm + c0 * PLD + o, PLD, -1.0, true,
+                                         n_tiles, lane);
                 }
             }
-            if (warp == 1) warp_inverse32(Dblk, PLD, scratch + (kb + 1) * 32 * SLD, rdiag, bars, (kb + 1) & 1, lane);
+            // block column kb of L (diagonal block and panel) and block kb of the inverse are final: to global memory now,
+            // underneath the factorisation of the next block (a single SM stores ~32 B/clk, 80 KB at the end would be 2.7k cycles)
+            const int t5 = bg * 32 + lane;
+            for (int q = t5; q < (PT - o) * 16; q += 160) {
+                const int i = o + (q >> 4), ch = (q & 15) * 2;
+                *reinterpret_cast<double2*>(A + (int64_t)i * ld + o + ch) = *reinterpret_cast<const double2*>(sm + i * PLD + o + ch);
+            }
+            for (int q = t5; q < 32 * 16; q += 160) {
+                const int i = q >> 4, ch = (q & 15) * 2;
+                *reinterpret_cast<double2*>(invd + (o + i) * PT + o + ch) = *reinterpret_cast<const double2*>(scratch + (kb * 32 + i) * SLD + ch);
+            }
         }
         __syncthreads();
         POTF2_STAMP(4 + 2 * kb);
     }
     POTF2_STAMP(9);
-    // L -> global: the ten lower 32-blocks (16-byte stores; the diagonal blocks carry their zeros above the diagonal from
-    // the factoring warp).  The strictly upper blocks of the tile keep their input values: no kernel reads them.
-#pragma unroll 4
-    for (int q = tid; q < 10 * 512; q += 256) {
-        const int blk = q >> 9, r = (q >> 4) & 31, ch = (q & 15) * 2;
-        const int rb = blk < 1 ? 0 : blk < 3 ? 1 : blk < 6 ? 2 : 3, cb = blk - rb * (rb + 1) / 2;
-        const int i = 32 * rb + r, j2 = 32 * cb + ch;
-        *reinterpret_cast<double2*>(A + (int64_t)i * ld + j2) = *reinterpret_cast<const double2*>(sm + i * PLD + j2);
+    // the last diagonal block of L and of the inverse (everything else was stored underneath the factorisation)
+    for (int q = tid; q < 32 * 16; q += 256) {
+        const int i = q >> 4, ch = (q & 15) * 2;
+        *reinterpret_cast<double2*>(A + (int64_t)(96 + i) * ld + 96 + ch) = *reinterpret_cast<const double2*>(sm + (96 + i) * PLD + 96 + ch);
+        *reinterpret_cast<double2*>(invd + (96 + i) * PT + 96 + ch) = *reinterpret_cast<const double2*>(scratch + (3 * 32 + i) * SLD + ch);
     }
     POTF2_STAMP(10);
-    // the four diagonal blocks of inv(L) -> invd: all that the block TRSM of the panel reads.  The rest of the inverse tile
-    // (needed by the L^-T products of the gradient only) is completed off the critical path by k_tile_inv.
-    for (int e = tid; e < 4 * 32 * 16; e += 256) {
-        const int kb = e >> 9, i = (e >> 4) & 31, j2 = (e & 15) * 2;
-        *reinterpret_cast<double2*>(invd + (32 * kb + i) * PT + 32 * kb + j2) =
-            *reinterpret_cast<const double2*>(scratch + (kb * 32 + i) * SLD + j2);
-    }
     POTF2_STAMP(11);
     POTF2_STAMP(12);
 }
@@ -1239,7 +1242,7 @@ int potrf_lower(double* A, int64_t ld, int64_t n, int64_t m_extra, double* invd,
         return PIGP_EINVAL;
     }
     const int T = (int)(n / TILE);
-    const int W = T < 12 ? 0 : T < 64 ? 2 : T < 128 ? 4 : 8;  // same rule as the solver's NLL-only evaluation
+    const int W = T < 12 ? 0 : T < 64 ? 2 : T < 128 ? 4 : 16;  // same rule as the solver's NLL-only evaluation
     if (W > 0) PIGP_TRY(chol_panels(A, ld, n, m_extra, invd, info, W, st));
     else PIGP_TRY(chol_rec(A, ld, n, m_extra, invd, info, 0, st));
     // the factorisation leaves the diagonal 32-blocks of the inverse tiles; callers of this entry point get complete tiles

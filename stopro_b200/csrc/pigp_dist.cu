@@ -107,8 +107,10 @@ __global__ void __launch_bounds__(256) k_push_diag(const double* invk, const dou
             const double2 v = *reinterpret_cast<const double2*>(invk + i * 128 + j2);
             for (int p = 0; p < pd.n; ++p) *reinterpret_cast<double2*>(pd.invd[p] + i * 128 + j2) = v;
         }
-        const double2 l = *reinterpret_cast<const double2*>(Lkk + (int64_t)i * ld + j2);
-        for (int p = 0; p < pd.n; ++p) *reinterpret_cast<double2*>(pd.lkk[p] + (int64_t)i * ld + j2) = l;
+        if ((j2 >> 5) <= (i >> 5)) {  // the lower 32-blocks of L_kk (k_potf2 does not define the others)
+            const double2 l = *reinterpret_cast<const double2*>(Lkk + (int64_t)i * ld + j2);
+            for (int p = 0; p < pd.n; ++p) *reinterpret_cast<double2*>(pd.lkk[p] + (int64_t)i * ld + j2) = l;
+        }
     }
     push_done(sg);
 }
@@ -522,7 +524,7 @@ static int lookahead_width(const pigp_dsolver* s, bool grad) {
     if (g_lookahead >= 0) return g_lookahead;
     if (s->world != 1 || s->T < 12) return 0;
     if (grad) return (s->T >= 16 && s->T < 32) ? 2 : (s->T >= 32 && s->T < 96) ? 4 : 0;  // -6 % at N = 2640, -4 % at 5018
-    return s->T < 64 ? 2 : s->T < 128 ? 4 : 8;
+    return s->T < 64 ? 2 : s->T < 128 ? 4 : 16;
 }
 
 static int ensure_lookahead(pigp_dsolver* s) {

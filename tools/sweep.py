@@ -104,7 +104,10 @@ def measure(cfg, label, reps, with_library=True):
         t_inv = timeit(lambda: torch.cholesky_inverse(L), max(1, reps // 2))
         rec["potrf"] = {"n": n, "ours_ms": t_ours, "ours_tflops": n ** 3 / 3 / t_ours * 1e-9, "cusolver_ms": t_lib,
                         "cusolver_tflops": n ** 3 / 3 / t_lib * 1e-9, "torch_cholesky_inverse_ms": t_inv,
-                        "library_nll_grad_floor_ms": t_lib + t_inv}
+                        "library_nll_grad_floor_ms": t_lib + t_inv,
+                        # the product path beside it: a whole NLL-only evaluation (assembly + factorisation + solve +
+                        # log-det) and a whole NLL + gradient evaluation at N <= n
+                        "nll_only_eval_ms": ms_nll, "nll_grad_eval_ms": ms_stream}
         del S, buf, L
         torch.cuda.empty_cache()
     return rec
