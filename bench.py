@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "NLL+grad evals/s at N=20k"
 UNIT = "evals/s"
-NCU_TRAFFIC_BYTES = 27.25e9  # profiles/r02_gemm_launches_summary.txt (dram read 25.66 GB + write 1.59 GB, re-captured on the round's code)
+NCU_TRAFFIC_BYTES = 27.08e9  # profiles/r02_gemm_full_summary.txt (dram read 25.48 GB + write 1.59 GB; ncu --set full on the round's final code)
 FP64_PEAK_FALLBACK = 36.45  # TFLOP/s, cuBLAS DGEMM 16384^3 on this pool's B200 (profiles/r01_fp64_peak.json)
 
 
@@ -439,9 +439,9 @@ def run_ours(args):
                      "traffic": NCU_TRAFFIC_BYTES if world == 1 else None,
                      "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the largest k_gemm launch of a step "
                                      "(K^-1 = Y Y^T, 78.6 ms, N^3/3 flops) from the ncu launch list of this round's code "
-                                     "(profiles/r02_gemm_launches_summary.txt; not measurable inside bench.py): that launch "
+                                     "(profiles/r02_gemm_full_summary.txt; not measurable inside bench.py): that launch "
                                      "reads 8.5x its algorithmic 3.2 GB (L2 hit rate 82 %) but uses 5 % of HBM bandwidth "
-                                     "(FP64 tensor pipe 94 % busy, profiles/r01_v2_gemm_full_summary.txt)",
+                                     "(tensor pipe 93 % busy, same capture)",
                      "kernel": "pigp::k_gemm / k_gemm_s (mma.sync.m8n8k4.f64 / DMMA.8x8x4)",
                      "peak_source": peak_src,
                      "algorithmic_flops_per_step": algorithmic_flops,

@@ -47,7 +47,19 @@ static void add_tiles(std::vector<AsmTile>& out, int64_t r0, int64_t r1, int64_t
     }
 }
 
+// (row cap of a tile: ASM_TR = 64 rows, or 16 when that leaves fewer tiles than two per SM -- the kernels of a small problem
+// are latency bound, and a CTA's time is proportional to its rows)
+static void build_lower_tiles_capped(const pigp_plan* p, int rank, int world, int row_cap, std::vector<AsmTile>& out);
+
 void build_lower_tiles_owned(const pigp_plan* p, int rank, int world, std::vector<AsmTile>& out) {
+    build_lower_tiles_capped(p, rank, world, ASM_TR, out);
+    if ((int64_t)out.size() < 2 * 148) {
+        out.clear();
+        build_lower_tiles_capped(p, rank, world, 16, out);
+    }
+}
+
+static void build_lower_tiles_capped(const pigp_plan* p, int rank, int world, int row_cap, std::vector<AsmTile>& out) {
     const int nb = p->n_row_blocks;
     for (int i = 0; i < nb; ++i)
         for (int j = 0; j <= i; ++j) {
@@ -56,7 +68,7 @@ void build_lower_tiles_owned(const pigp_plan* p, int rank, int world, std::vecto
             const int flags = (i == j) ? ASM_LOWER : ASM_SWAP;
             const int64_t r1 = p->sec_row[i + 1], c0 = p->sec_row[j], c1 = p->sec_row[j + 1];
             for (int64_t r = p->sec_row[i]; r < r1;) {
-                const int nr = (int)std::min<int64_t>(std::min<int64_t>(ASM_TR, r1 - r), TILE - r % TILE);
+                const int nr = (int)std::min<int64_t>(std::min<int64_t>(row_cap, r1 - r), TILE - r % TILE);
                 if ((int)((r / TILE) % world) == rank)
                     for (int64_t c = c0; c < c1; c += ASM_TC) {
                         if ((flags & ASM_LOWER) && r + nr - 1 < c) continue;

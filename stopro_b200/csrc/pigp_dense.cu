@@ -1025,7 +1025,7 @@ __global__ void __launch_bounds__(256, 1) k_potf2(double* A, int64_t ld, double*
 //   the two 64 x 64 diagonal halves from their 32-blocks, W_ba = -inv(L_b) (L_ba inv(L_a)); then W21 = -W22 (L21 W11), with
 //   the (unused) upper-right 64 x 64 quadrant of the tile as scratch for L21 W11.
 // Optionally also writes the tile transposed into Yt (the diagonal tile of Y = L^-T, zeros below its diagonal).
-__global__ void __launch_bounds__(256, 1) k_tile_inv(const double* L, int64_t ld, double* invd, int first, int stride, double* Y, int64_t ldy) {
+__global__ void __launch_bounds__(256, 1) k_tile_inv(const double* L, int64_t ld, double* invd, int first, int stride, double* Y, int64_t ldy, int zero_upper) {
     extern __shared__ __align__(16) double sm[];
     double* scratch = sm + PT * PLD;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1092,10 +1092,10 @@ __global__ void __launch_bounds__(256, 1) k_tile_inv(const double* L, int64_t ld
 #pragma unroll 8
     for (int q = tid; q < PT * PT / 2; q += 256) {
         const int i = q >> 6, j2 = (q & 63) * 2;
-        double2 v = *reinterpret_cast<const double2*>(sm + i * PLD + j2);
-        if (j2 > i) v.x = 0.0;
-        if (j2 + 1 > i) v.y = 0.0;
-        *reinterpret_cast<double2*>(W + i * PT + j2) = v;
+        // the strictly lower 32-blocks: the diagonal blocks are in place (and may be being read by the panel's TRSM); the
+        // blocks above are zero in the solver's workspace and are cleared here for caller-provided buffers (zero_upper)
+        if ((j2 >> 5) < (i >> 5)) *reinterpret_cast<double2*>(W + i * PT + j2) = *reinterpret_cast<const double2*>(sm + i * PLD + j2);
+        else if (zero_upper && (j2 >> 5) > (i >> 5)) *reinterpret_cast<double2*>(W + i * PT + j2) = make_double2(0.0, 0.0);
     }
     if (Y) {
         double* Yt = Y + (int64_t)c * PT * ldy + (int64_t)c * PT;
@@ -1106,7 +1106,7 @@ __global__ void __launch_bounds__(256, 1) k_tile_inv(const double* L, int64_t ld
     }
 }
 
-int launch_tile_inv(const double* L, int64_t ld, double* invd, int first, int stride, int count, double* Y, int64_t ldy, cudaStream_t st) {
+int launch_tile_inv(const double* L, int64_t ld, double* invd, int first, int stride, int count, double* Y, int64_t ldy, cudaStream_t st, int zero_upper) {
     if (count <= 0) return PIGP_OK;
     static bool attr_done[64] = {};
     int dev = 0;
@@ -1116,7 +1116,7 @@ int launch_tile_inv(const double* L, int64_t ld, double* invd, int first, int st
         attr_done[dev & 63] = true;
     }
     ProfScope prof(PROF_POTF2, st);
-    k_tile_inv<<<(unsigned)count, 256, POTF2_SMEM, st>>>(L, ld, invd, first, stride, Y, ldy);
+    k_tile_inv<<<(unsigned)count, 256, POTF2_SMEM, st>>>(L, ld, invd, first, stride, Y, ldy, zero_upper);
     count_launch();
     PIGP_CUDA(cudaGetLastError());
     return PIGP_OK;
@@ -1246,7 +1246,7 @@ int potrf_lower(double* A, int64_t ld, int64_t n, int64_t m_extra, double* invd,
     if (W > 0) PIGP_TRY(chol_panels(A, ld, n, m_extra, invd, info, W, st));
     else PIGP_TRY(chol_rec(A, ld, n, m_extra, invd, info, 0, st));
     // the factorisation leaves the diagonal 32-blocks of the inverse tiles; callers of this entry point get complete tiles
-    return launch_tile_inv(A, ld, invd, 0, 1, (int)(n / TILE), nullptr, 0, st);
+    return launch_tile_inv(A, ld, invd, 0, 1, (int)(n / TILE), nullptr, 0, st, 1);
 }
 
 // ----------------------------------------------------------------------------------------------- TRTRI + LAUUM

@@ -269,8 +269,9 @@ struct pigp_dsolver {
     // internal streams: `sa` (high priority) carries the latency-bound Cholesky chain, `sb` the Y = L^-T products that
     // depend only on finished panels, so that they fill the bubbles of the chain
     cudaStream_t sa = nullptr, sb = nullptr, sc = nullptr;  // sc: publication kernels (peer stores), off the chain
-    cudaEvent_t ev_in = nullptr, ev_bar = nullptr, ev_b = nullptr, ev_c = nullptr, ev_out = nullptr;
-    std::vector<cudaEvent_t> ev_diag, ev_upd;
+    cudaEvent_t ev_in = nullptr, ev_bar = nullptr, ev_b = nullptr, ev_c = nullptr, ev_out = nullptr, ev_y0 = nullptr;
+    std::vector<cudaEvent_t> ev_diag, ev_upd, ev_inv;
+    cudaStream_t se = nullptr;  // completes the inverse diagonal tiles (k_tile_inv) as soon as L_kk exists, off both chains
     cudaStream_t sd = nullptr;                // bulk trailing updates of the panel schedule
     std::vector<cudaEvent_t> ev_pan, ev_next; // per coarse panel: chain done / next panel's columns updated
     cudaEvent_t ev_d = nullptr;
@@ -302,6 +303,7 @@ struct Ctx {
     cudaStream_t st;   // chain stream
     cudaStream_t sb;   // side stream (Y = L^-T), used when grad is set
     cudaStream_t sc;   // publication stream
+    cudaStream_t se;   // inverse-tile stream
     bool grad;
     PeerFlags pf;
     int npeers;
@@ -430,9 +432,12 @@ int leaf(const Ctx& c, int k) {
     if (c.grad) {
         // Y[j, k] = R[j, k] inv(L_kk)^T for own row tiles j < k; Y[k, k] = inv(L_kk)^T.  The factorisation only produced
         // the diagonal 32-blocks of inv(L_kk); every rank completes the tile itself from its copy of L_kk, here, off the chain
-        PIGP_CUDA(cudaStreamWaitEvent(c.sb, s->ev_diag[k], 0));
-        if (!mine) PIGP_TRY(wait_one(c, s->f_diag(k), c.sb));
-        PIGP_TRY(launch_tile_inv(s->L, ld, s->invd, k, 1, 1, mine ? s->Y : nullptr, ld, c.sb));
+        // (on its own stream: it depends on L_kk only, so it runs ahead of the L^-T chain instead of inside it)
+        PIGP_CUDA(cudaStreamWaitEvent(c.se, s->ev_diag[k], 0));
+        if (!mine) PIGP_TRY(wait_one(c, s->f_diag(k), c.se));
+        PIGP_TRY(launch_tile_inv(s->L, ld, s->invd, k, 1, 1, mine ? s->Y : nullptr, ld, c.se));
+        PIGP_CUDA(cudaEventRecord(s->ev_inv[k], c.se));
+        PIGP_CUDA(cudaStreamWaitEvent(c.sb, s->ev_inv[k], 0));
         const int first = s->first_own(0), cnt = s->count_own(0, k);
         if (cnt > 0) {
             GemmDesc g{};
@@ -629,9 +634,11 @@ void pigp_dsolver_destroy(pigp_dsolver* s) {
     if (s->ev_d) cudaEventDestroy(s->ev_d);
     for (cudaEvent_t e : s->ev_pan) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : s->ev_next) if (e) cudaEventDestroy(e);
-    for (cudaEvent_t e : {s->ev_in, s->ev_bar, s->ev_b, s->ev_c, s->ev_out}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {s->ev_in, s->ev_bar, s->ev_b, s->ev_c, s->ev_out, s->ev_y0}) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : s->ev_diag) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : s->ev_upd) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : s->ev_inv) if (e) cudaEventDestroy(e);
+    if (s->se) cudaStreamDestroy(s->se);
     delete s;
 }
 
@@ -704,12 +711,15 @@ int pigp_dsolver_create(pigp_plan* plan, int rank, int world, pigp_dsolver** out
         cuda_ok(cudaStreamCreateWithPriority(&s->sa, cudaStreamNonBlocking, hi), "cudaStreamCreate sa");
         cuda_ok(cudaStreamCreateWithPriority(&s->sb, cudaStreamNonBlocking, lo), "cudaStreamCreate sb");
         cuda_ok(cudaStreamCreateWithPriority(&s->sc, cudaStreamNonBlocking, hi), "cudaStreamCreate sc");
-        for (cudaEvent_t* e : {&s->ev_in, &s->ev_bar, &s->ev_b, &s->ev_c, &s->ev_out}) cuda_ok(cudaEventCreateWithFlags(e, cudaEventDisableTiming), "cudaEventCreate");
+        for (cudaEvent_t* e : {&s->ev_in, &s->ev_bar, &s->ev_b, &s->ev_c, &s->ev_out, &s->ev_y0}) cuda_ok(cudaEventCreateWithFlags(e, cudaEventDisableTiming), "cudaEventCreate");
         s->ev_diag.assign(s->T, nullptr);
         s->ev_upd.assign(s->T, nullptr);
+        s->ev_inv.assign(s->T, nullptr);
+        cuda_ok(cudaStreamCreateWithPriority(&s->se, cudaStreamNonBlocking, lo), "cudaStreamCreate se");
         for (int k = 0; k < s->T; ++k) {
             cuda_ok(cudaEventCreateWithFlags(&s->ev_diag[k], cudaEventDisableTiming), "cudaEventCreate");
             cuda_ok(cudaEventCreateWithFlags(&s->ev_upd[k], cudaEventDisableTiming), "cudaEventCreate");
+            cuda_ok(cudaEventCreateWithFlags(&s->ev_inv[k], cudaEventDisableTiming), "cudaEventCreate");
         }
     }
     if (rc != PIGP_OK) { pigp_dsolver_destroy(s); return rc; }
@@ -837,6 +847,9 @@ static int dsolver_enqueue(pigp_dsolver* s, const double* theta_dev, const doubl
     const bool serial = !g_side_stream || (s->shared_device && s->world >= 3);
     c.sb = serial ? st : s->sb;
     c.sc = serial ? st : s->sc;
+    // ranks sharing one device (tests) keep the inverse tiles on the side stream: a fifth stream per rank with its own spinning
+    // flag waits would exceed the device's 8 hardware queues, and a producer queued behind a wait dead-locks until the time-out
+    c.se = serial ? st : (s->shared_device ? c.sb : s->se);
     c.grad = grad_dev != nullptr;
     int32_t* info = s->info;
     PIGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
@@ -851,6 +864,9 @@ static int dsolver_enqueue(pigp_dsolver* s, const double* theta_dev, const doubl
         if (cnt > 0)
             PIGP_CUDA(cudaMemset2DAsync(s->Y + (int64_t)first * TILE * ld, sizeof(double) * TILE * ld * s->world, 0,
                                         sizeof(double) * TILE * ld, cnt, c.sb));
+        // the inverse-tile stream writes the diagonal tiles of Y: behind the clearing of Y
+        PIGP_CUDA(cudaEventRecord(s->ev_y0, c.sb));
+        PIGP_CUDA(cudaStreamWaitEvent(c.se, s->ev_y0, 0));
     }
     // own rows of K (lower, jitter added), identity padding (owner of the last tile), own y tile
     PIGP_TRY(launch_assemble(p, s->d_tiles, s->n_tiles, theta_dev, eps, 1, s->L, ld, st));
@@ -949,6 +965,7 @@ int pigp_dsolver_reset(pigp_dsolver* s) {
     PIGP_CUDA(cudaStreamSynchronize(s->sa));
     PIGP_CUDA(cudaStreamSynchronize(s->sb));
     PIGP_CUDA(cudaStreamSynchronize(s->sc));
+    PIGP_CUDA(cudaStreamSynchronize(s->se));
     PIGP_CUDA(cudaMemset(s->err, 0, sizeof(int)));
     PIGP_CUDA(cudaMemset(s->sig_counter, 0, 2 * sizeof(unsigned int)));
     // the ranks' call counters may have drifted apart (a rank that never made the failed call): everybody restarts at

@@ -209,7 +209,8 @@ int launch_gemm(const GemmDesc& g, cudaStream_t st);
 int launch_potf2(double* A, int64_t ld, double* invd, int32_t* info, int base, cudaStream_t st);
 // complete the inverse tiles c = first + i * stride (i < count) from L_cc and their diagonal blocks; Y != nullptr: also
 // write inv(L_cc)^T into the diagonal tile c of Y (row stride ldy)
-int launch_tile_inv(const double* L, int64_t ld, double* invd, int first, int stride, int count, double* Y, int64_t ldy, cudaStream_t st);
+int launch_tile_inv(const double* L, int64_t ld, double* invd, int first, int stride, int count, double* Y, int64_t ldy, cudaStream_t st,
+                    int zero_upper = 0);
 int potrf_lower(double* A, int64_t ld, int64_t n, int64_t m_extra, double* invd, int32_t* info, cudaStream_t st);
 int potri_lower(const double* L, int64_t ld, int64_t n, const double* invd, double* W, double* X, cudaStream_t st);
 // out[0] = sum_{i<n} log A[i*ld+i]; out[1] = sum_{j<n} v[j]^2  (v = row `vrow` of A)

@@ -13,6 +13,7 @@ hdr, units = rows[0], rows[1]
 KEYS = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "dram__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__shared_mem_per_block_static",
         "launch__occupancy_limit_registers", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "sass__inst_executed_local_loads", "lts__t_sector_hit_rate.pct",
