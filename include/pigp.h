@@ -27,6 +27,8 @@
  *   PIGP_FUSE_WAITS=1     spin on the DIAG flag inside the consuming TRSM instead of a one-CTA wait kernel
  *   PIGP_PROF_DUMP=<csv>  per-launch timeline written by pigp_profile_stop
  *   PIGP_LOOKAHEAD=<W>    panel schedule with look-ahead, W tile columns per panel (see pigp_set_lookahead)
+ *   PIGP_EARLY_KINV=0     compute K^-1 = Y Y^T in one product at the end instead of accumulating it from finished column ranges
+ *                         of Y underneath the factorisation (single GPU, 8..32 tiles; costs one more N^2 buffer)
  *   PIGP_WAIT_TIMEOUT_S / PIGP_BARRIER_TIMEOUT_S   flag-wait limits of the multi-GPU path (see pigp_dsolver_reset)
  */
 #ifndef PIGP_H

@@ -271,6 +271,12 @@ struct pigp_dsolver {
     cudaStream_t sa = nullptr, sb = nullptr, sc = nullptr;  // sc: publication kernels (peer stores), off the chain
     cudaEvent_t ev_in = nullptr, ev_bar = nullptr, ev_b = nullptr, ev_c = nullptr, ev_out = nullptr, ev_y0 = nullptr;
     std::vector<cudaEvent_t> ev_diag, ev_upd, ev_inv;
+    // single-rank, mid-size problems: K^-1 = Y Y^T accumulates in its own buffer from column ranges of Y as they become final,
+    // on a low-priority stream underneath the latency-bound chains, instead of one product at the end
+    double* Kinv = nullptr;
+    cudaStream_t sk = nullptr;
+    cudaEvent_t ev_k = nullptr, ev_kd = nullptr;
+    int k_done = 0;
     cudaStream_t se = nullptr;  // completes the inverse diagonal tiles (k_tile_inv) as soon as L_kk exists, off both chains
     cudaStream_t sd = nullptr;                // bulk trailing updates of the panel schedule
     std::vector<cudaEvent_t> ev_pan, ev_next; // per coarse panel: chain done / next panel's columns updated
@@ -304,6 +310,9 @@ struct Ctx {
     cudaStream_t sb;   // side stream (Y = L^-T), used when grad is set
     cudaStream_t sc;   // publication stream
     cudaStream_t se;   // inverse-tile stream
+    cudaStream_t sk;   // early K^-1 products
+    bool early_kinv;
+    int kinv_gran;
     bool grad;
     PeerFlags pf;
     int npeers;
@@ -450,6 +459,24 @@ int leaf(const Ctx& c, int k) {
             g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = k; g.k_gt0 = k;
             g.force_bn128 = 1;
             PIGP_TRY(launch_gemm(g, c.sb));
+        }
+        // columns [k_done, k + 1) of Y are final once the side stream gets here: their share of K^-1 = Y Y^T,
+        //   Kinv[i, j] += sum_{k in range, k >= i} Y[i, k] Y[j, k]   (rows / columns 0 .. k, lower part),
+        // goes to the low-priority product stream now, while the chains are still running
+        if (c.early_kinv && (k + 1 - s->k_done >= c.kinv_gran || k + 1 == s->T)) {
+            const int a = s->k_done, b = k + 1;
+            PIGP_CUDA(cudaEventRecord(s->ev_k, c.sb));
+            PIGP_CUDA(cudaStreamWaitEvent(c.sk, s->ev_k, 0));
+            GemmDesc g{};
+            g.M = b * TILE; g.N = b * TILE; g.K = (b - a) * TILE;
+            g.alpha = 1.0; g.beta = 1.0;
+            g.A = s->Y + (int64_t)a * TILE; g.lda = ld; g.a_kcontig = 1;
+            g.B = s->Y + (int64_t)a * TILE; g.ldb = ld; g.b_kcontig = 1;
+            g.C = s->Kinv; g.ldc = ld;
+            g.lower_only = 1; g.kmode = 1;
+            g.gen = 1; g.m_ts = 1; g.m_gt0 = 0; g.n_gt0 = 0; g.k_gt0 = a;
+            PIGP_TRY(launch_gemm(g, c.sk));
+            s->k_done = b;
         }
     }
     return PIGP_OK;
@@ -639,6 +666,10 @@ void pigp_dsolver_destroy(pigp_dsolver* s) {
     for (cudaEvent_t e : s->ev_upd) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : s->ev_inv) if (e) cudaEventDestroy(e);
     if (s->se) cudaStreamDestroy(s->se);
+    if (s->sk) cudaStreamDestroy(s->sk);
+    if (s->ev_k) cudaEventDestroy(s->ev_k);
+    if (s->ev_kd) cudaEventDestroy(s->ev_kd);
+    cudaFree(s->Kinv);
     delete s;
 }
 
@@ -716,6 +747,9 @@ int pigp_dsolver_create(pigp_plan* plan, int rank, int world, pigp_dsolver** out
         s->ev_upd.assign(s->T, nullptr);
         s->ev_inv.assign(s->T, nullptr);
         cuda_ok(cudaStreamCreateWithPriority(&s->se, cudaStreamNonBlocking, lo), "cudaStreamCreate se");
+        cuda_ok(cudaStreamCreateWithPriority(&s->sk, cudaStreamNonBlocking, lo), "cudaStreamCreate sk");
+        cuda_ok(cudaEventCreateWithFlags(&s->ev_k, cudaEventDisableTiming), "cudaEventCreate");
+        cuda_ok(cudaEventCreateWithFlags(&s->ev_kd, cudaEventDisableTiming), "cudaEventCreate");
         for (int k = 0; k < s->T; ++k) {
             cuda_ok(cudaEventCreateWithFlags(&s->ev_diag[k], cudaEventDisableTiming), "cudaEventCreate");
             cuda_ok(cudaEventCreateWithFlags(&s->ev_upd[k], cudaEventDisableTiming), "cudaEventCreate");
@@ -851,6 +885,16 @@ static int dsolver_enqueue(pigp_dsolver* s, const double* theta_dev, const doubl
     // flag waits would exceed the device's 8 hardware queues, and a producer queued behind a wait dead-locks until the time-out
     c.se = serial ? st : (s->shared_device ? c.sb : s->se);
     c.grad = grad_dev != nullptr;
+    c.sk = serial ? st : s->sk;
+    {
+        static int early = -1;  // PIGP_EARLY_KINV=0 switches the early products off
+        if (early < 0) { const char* e = getenv("PIGP_EARLY_KINV"); early = (e && atoi(e) == 0) ? 0 : 1; }
+        // worth it while the evaluation is latency bound and its GEMMs are short: -9 % at N = 1180, -7.5 % at 2640.  From
+        // N ~ 5000 on nothing is gained (measured 5018 ... 12700): the product's CTAs then hold every SM for tens of
+        // microseconds, and each of the chains' launches waits that long for a slot -- priorities do not pre-empt
+        c.early_kinv = early && c.grad && s->world == 1 && s->T >= 8 && s->T <= 32;
+        c.kinv_gran = std::max(2, s->T / 8);
+    }
     int32_t* info = s->info;
     PIGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
     // every peer has finished reading what the previous call left in this rank's buffers
@@ -867,6 +911,12 @@ static int dsolver_enqueue(pigp_dsolver* s, const double* theta_dev, const doubl
         // the inverse-tile stream writes the diagonal tiles of Y: behind the clearing of Y
         PIGP_CUDA(cudaEventRecord(s->ev_y0, c.sb));
         PIGP_CUDA(cudaStreamWaitEvent(c.se, s->ev_y0, 0));
+        if (c.early_kinv) {
+            if (!s->Kinv) PIGP_CUDA(cudaMalloc(&s->Kinv, sizeof(double) * (size_t)s->npad * s->ld));
+            PIGP_CUDA(cudaStreamWaitEvent(c.sk, s->ev_bar, 0));  // the previous evaluation's gradient kernel has read Kinv
+            PIGP_CUDA(cudaMemsetAsync(s->Kinv, 0, sizeof(double) * (size_t)s->npad * s->ld, c.sk));
+            s->k_done = 0;
+        }
     }
     // own rows of K (lower, jitter added), identity padding (owner of the last tile), own y tile
     PIGP_TRY(launch_assemble(p, s->d_tiles, s->n_tiles, theta_dev, eps, 1, s->L, ld, st));
@@ -925,8 +975,11 @@ static int dsolver_enqueue(pigp_dsolver* s, const double* theta_dev, const doubl
             count_launch(2);
         }
         PIGP_CUDA(cudaGetLastError());
-        // own row tiles of K^-1 = Y Y^T (lower) over the own rows of L
-        if (cnt > 0) {
+        // own row tiles of K^-1 = Y Y^T (lower) over the own rows of L -- unless it was accumulated along the way
+        if (c.early_kinv) {
+            PIGP_CUDA(cudaEventRecord(s->ev_kd, c.sk));
+            PIGP_CUDA(cudaStreamWaitEvent(st, s->ev_kd, 0));
+        } else if (cnt > 0) {
             GemmDesc g{};
             g.M = cnt * TILE; g.N = (int)s->npad; g.K = (int)s->npad;
             g.alpha = 1.0; g.beta = 0.0;
@@ -937,7 +990,7 @@ static int dsolver_enqueue(pigp_dsolver* s, const double* theta_dev, const doubl
             g.gen = 1; g.m_ts = s->world; g.m_gt0 = first; g.n_gt0 = 0; g.k_gt0 = 0;
             PIGP_TRY(launch_gemm(g, st));
         }
-        PIGP_TRY(launch_grad(p, s->d_tiles, s->n_tiles, theta_dev, s->L, ld, s->alpha, s->partials, s->gpart, st));
+        PIGP_TRY(launch_grad(p, s->d_tiles, s->n_tiles, theta_dev, c.early_kinv ? s->Kinv : s->L, ld, s->alpha, s->partials, s->gpart, st));
         {
             PeerBufs pb{};
             pb.n = c.npeers;
@@ -966,6 +1019,7 @@ int pigp_dsolver_reset(pigp_dsolver* s) {
     PIGP_CUDA(cudaStreamSynchronize(s->sb));
     PIGP_CUDA(cudaStreamSynchronize(s->sc));
     PIGP_CUDA(cudaStreamSynchronize(s->se));
+    PIGP_CUDA(cudaStreamSynchronize(s->sk));
     PIGP_CUDA(cudaMemset(s->err, 0, sizeof(int)));
     PIGP_CUDA(cudaMemset(s->sig_counter, 0, 2 * sizeof(unsigned int)));
     // the ranks' call counters may have drifted apart (a rank that never made the failed call): everybody restarts at
