@@ -115,18 +115,6 @@ __global__ void __launch_bounds__(256) k_push_diag(const double* invk, const dou
     push_done(sg);
 }
 
-// diagonal tile c of Y <- inv(L_cc)^T (full tile: zeros below the diagonal)
-__global__ void __launch_bounds__(256) k_place_diag_t(double* Y, int64_t ld, const double* invd, int first, int stride) {
-    const int c = first + (blockIdx.x >> 4) * stride;
-    double* dst = Y + (int64_t)c * 128 * ld + (int64_t)c * 128;
-    const double* src = invd + (int64_t)c * 128 * 128;
-    __shared__ double sh[32][33];
-    const int bi = (blockIdx.x >> 2) & 3, bj = blockIdx.x & 3;  // one 32 x 32 sub-block per CTA
-    for (int e = threadIdx.x; e < 1024; e += 256) sh[e >> 5][e & 31] = src[(bi * 32 + (e >> 5)) * 128 + bj * 32 + (e & 31)];
-    __syncthreads();
-    for (int e = threadIdx.x; e < 1024; e += 256) dst[(int64_t)(bj * 32 + (e >> 5)) * ld + bi * 32 + (e & 31)] = sh[e & 31][e >> 5];
-}
-
 // alpha[j] = sum_{k >= tile(j) * 128} Y[j][k] v[k]   (one warp per row; Y upper triangular by tiles)
 __global__ void __launch_bounds__(256) k_gemv_upper(const double* Y, int64_t ld, int64_t npad, const double* v, double* alpha) {
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -637,7 +625,7 @@ int preload_dist() {
     PIGP_TRY(preload_dense());
     PIGP_TRY(preload_assemble());
     PIGP_TRY(preload_matern());
-    PIGP_PRELOAD(k_signal); PIGP_PRELOAD(k_wait); PIGP_PRELOAD(k_push_rows); PIGP_PRELOAD(k_place_diag_t);
+    PIGP_PRELOAD(k_signal); PIGP_PRELOAD(k_wait); PIGP_PRELOAD(k_push_rows);
     PIGP_PRELOAD(k_gemv_upper); PIGP_PRELOAD(k_set_ytile); PIGP_PRELOAD(k_push_vec); PIGP_PRELOAD(k_sum_slots);
     PIGP_PRELOAD(k_finish_nll_d); PIGP_PRELOAD(k_diag_info); PIGP_PRELOAD(k_copy_v); PIGP_PRELOAD(k_push_panel); PIGP_PRELOAD(k_push_diag);
     return PIGP_OK;
