@@ -193,3 +193,62 @@ def test_dense_building_blocks(cuda_device):
     _lib.check(lib.pigp_potrf_lower(bad.data_ptr(), 128, 128, 0, invd.data_ptr(), info.data_ptr(), None))
     torch.cuda.synchronize()
     assert int(info.item()) == 1 and torch.isnan(bad[0, 0])
+
+
+def test_panel_schedule_of_the_standalone_factorisation(cuda_device):
+    """pigp_potrf_lower takes the panel schedule with look-ahead from 12 tiles on (two streams, coarse panels): factor, extra
+    rows and inverse tiles against torch / cuSOLVER at 16 tiles, in a caller-provided (uninitialised) workspace."""
+    import torch
+
+    from stopro_b200 import _lib
+
+    lib = _lib.lib()
+    n, extra = 2048, 256
+    g = torch.Generator(device=cuda_device).manual_seed(5)
+    X = torch.randn(n, n + 64, dtype=torch.float64, device=cuda_device, generator=g)
+    S = X @ X.t() / n + torch.eye(n, dtype=torch.float64, device=cuda_device)
+    E = torch.randn(extra, n, dtype=torch.float64, device=cuda_device, generator=g)
+    buf = torch.cat([S, E], 0).contiguous()
+    invd = torch.full((n // 128, 128, 128), float("nan"), dtype=torch.float64, device=cuda_device)
+    info = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+    for _ in range(2):  # twice: the second call reuses the cached bulk stream and events
+        buf.copy_(torch.cat([S, E], 0))
+        _lib.check(lib.pigp_potrf_lower(buf.data_ptr(), n, n, extra, invd.data_ptr(), info.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert int(info.item()) == 0
+    Lref = torch.linalg.cholesky(S)
+    assert relerr(torch.tril(buf[:n]).cpu().numpy(), Lref.cpu().numpy()) < 1e-12
+    Eref = torch.linalg.solve_triangular(Lref, E.t(), upper=False).t()
+    assert relerr(buf[n:].cpu().numpy(), Eref.cpu().numpy()) < 1e-11
+    eye = torch.eye(128, dtype=torch.float64, device=cuda_device)
+    for k in (0, 7, 15):
+        W = invd[k]
+        assert not torch.isnan(W).any() and float(torch.triu(W, 1).abs().max()) == 0.0
+        assert float((W @ Lref[128 * k:128 * (k + 1), 128 * k:128 * (k + 1)] - eye).abs().max()) < 1e-11
+
+
+@pytest.mark.parametrize("col", [0, 37, 200, 201, 255])
+def test_first_failing_pivot_is_reported(cuda_device, col):
+    """info = 1-based index of the first non-positive pivot, as LAPACK's potrf reports it -- for even and odd columns of
+    the 2 x 2 pivot blocks, and across 32-column blocks and 128-column tiles; everything from that column on is NaN."""
+    import torch
+
+    from stopro_b200 import _lib
+
+    lib = _lib.lib()
+    n = 256
+    g = torch.Generator(device=cuda_device).manual_seed(col)
+    X = torch.randn(n, n, dtype=torch.float64, device=cuda_device, generator=g)
+    S = X @ X.t() / n + torch.eye(n, dtype=torch.float64, device=cuda_device)
+    Lref = torch.linalg.cholesky(S)
+    # make the Schur complement at `col` negative: lower the diagonal entry below the sum of squares of its row of L
+    S[col, col] = (Lref[col, :col] ** 2).sum() - 0.5
+    buf = S.clone()
+    invd = torch.empty(n // 128, 128, 128, dtype=torch.float64, device=cuda_device)
+    info = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+    _lib.check(lib.pigp_potrf_lower(buf.data_ptr(), n, n, 0, invd.data_ptr(), info.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert int(info.item()) == col + 1
+    assert torch.isnan(buf[col, col])
+    if col > 0:
+        assert relerr(torch.tril(buf[:col, :col]).cpu().numpy(), Lref[:col, :col].cpu().numpy()) < 1e-12
