@@ -18,6 +18,8 @@ dev = torch.device("cuda:0")
 theta = torch.as_tensor(cfg["theta0"], device=dev)
 y = torch.as_tensor(cfg["delta_y"], device=dev)
 out = torch.zeros(1 + P, dtype=torch.float64, device=dev)
+if os.environ.get("PIGP_SERIAL"):  # every kernel on one stream: per-launch event times do not overlap
+    _lib.check(_lib.lib().pigp_set_side_stream(0))
 for it in range(2):
     if it == 1 and os.environ.get("PIGP_PROF_DUMP"):
         _lib.profile_start()
