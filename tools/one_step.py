@@ -10,6 +10,8 @@ from stopro_b200 import _lib, synthetic
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 cfg = synthetic.stokes2d_scaling(n, n_test=16)
+if len(sys.argv) > 2:  # optional jitter override (eps = 1 makes the workload well conditioned at any size)
+    cfg = dict(cfg, eps=float(sys.argv[2]))
 gp = synthetic.make_model(cfg)
 gp.set_constants(cfg["r_train"], cfg["delta_y"], cfg["eps"], only_training=True)
 solver = gp._solver_for(cfg["r_train"])
