@@ -15,6 +15,7 @@
 // * Host drivers: recursive right-looking Cholesky (all flops in k_gemm), TRTRI + LAUUM for K^-1.
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 #include "pigp_internal.cuh"
@@ -1183,7 +1184,8 @@ static int chol_rec(double* A, int64_t ld, int64_t n, int64_t m_below, double* i
 // of W tile columns, the recursion inside a panel (and its TRSM of all rows below) on the caller's stream, the panel's
 // update of the columns to its right on a bulk stream -- the next panel's columns first, the chain waits only for those.
 struct PanelStreams { cudaStream_t bulk = nullptr; std::vector<cudaEvent_t> pan, next; cudaEvent_t done = nullptr; };
-static PanelStreams g_panel_streams[64];
+static PanelStreams g_panel_streams[64];  // per device; the enqueue below holds g_panel_mutex (host threads share them)
+static std::mutex g_panel_mutex;
 
 static int panel_update_dense(double* A, int64_t ld, int64_t rows, int64_t j0, int64_t j1, int64_t c0, int64_t c1, cudaStream_t st) {
     // C[c0.., [c0, c1)] -= L[c0.., [j0, j1)] L[[c0, c1), [j0, j1)]^T for all `rows` rows from c0 down (lower part)
@@ -1202,6 +1204,7 @@ static int panel_update_dense(double* A, int64_t ld, int64_t rows, int64_t j0, i
 static int chol_panels(double* A, int64_t ld, int64_t n, int64_t m_extra, double* invd, int32_t* info, int W, cudaStream_t st) {
     int dev = 0;
     PIGP_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_panel_mutex);
     PanelStreams& ps = g_panel_streams[dev & 63];
     const int T = (int)(n / TILE), n_pan = (T + W - 1) / W;
     if (!ps.bulk) {
