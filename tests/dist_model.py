@@ -11,8 +11,8 @@ index arithmetic and the dependency structure of the N > 1 path can be checked o
     its rank yield, and "no rank can advance" is reported as a dead-lock;
   * a read of data that a peer has not published yet shows up as a wrong result (buffers start as NaN).
 
-`schedule="panels"` models the experimental look-ahead schedule (`chol_lookahead`, compiled only with
--DPIGP_EXPERIMENTAL_LOOKAHEAD).  The tile size is a parameter (4 in the tests instead of 128).
+`schedule="panels"` models the panel schedule with look-ahead (`chol_lookahead`, `pigp_set_lookahead`).  The tile size is
+a parameter (4 in the tests instead of 128).
 """
 import numpy as np
 
