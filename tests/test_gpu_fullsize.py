@@ -62,3 +62,21 @@ def test_two_ranks_reproduce_the_single_rank_result(problem):
     assert abs(out[0][0] - nll) <= 1e-10 * abs(nll)
     assert np.max(np.abs(out[0][1] - grad)) <= 1e-8 * np.max(np.abs(grad))
     assert out[1][0] == out[0][0] and np.array_equal(out[1][1], out[0][1])
+
+
+@pytest.mark.parametrize("n,eps,strict", [(4000, 1e-6, False), (4000, 1.0, True)])
+def test_bench_workload_parity_against_the_oracle(cuda_device, n, eps, strict):
+    """The parity object of the bench line as a test: NLL and gradient of the C5 workload itself (N = 4000 instance) through
+    the host entry point against the oracle on the same inputs.  With the benchmark's own eps = 1e-6 the matrix is near
+    singular (cond_1 ~ 1e14 from LAPACK dpocon), so agreement is held to max(1e-8, cond * u); with eps = 1 to 1e-8."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    _, _, _, ref = bench.cpu_reference_eval(n, n, repeats=1, keep=True, eps=eps)
+    par = bench.bench_parity(ref, None, strict=strict)
+    print(f"\n[bench workload N={n} eps={eps:g}] cond_1={par['cond_1norm']:.2e} nll {par['nll_relerr']:.2e} "
+          f"grad {par['grad_relerr']:.2e} tol {par['tolerance']:.2e}")
+    assert par["ok"], par
