@@ -722,17 +722,19 @@ int launch_gemm(const GemmDesc& g_in, cudaStream_t st) {
 }
 
 // ----------------------------------------------------------------------------------------------- POTF2 (128 x 128)
-// One CTA (8 warps) factors a 128 x 128 diagonal tile held in shared memory and inverts the factor in place.
-// Blocked with 32 x 32 blocks so that only 4 x 32 column steps are sequential:
-//   per block column kb: warp 0 factors the 32 x 32 diagonal block in registers (lane = row, columns exchanged by
-//   shuffles) and inverts it; all warps then form the panel  L_ik = A_ik inv(L_kk)^T  and the trailing update
-//   A_ij -= L_ik L_jk^T  as 8 x 32 strips of FP64 MMAs (DMMA) out of shared memory.
-//   inverse: the two 64 x 64 diagonal halves from their 32-blocks, then W21 = -W22 (L21 W11); the (zero) upper-right
+// k_potf2: one CTA (8 warps) factors a 128 x 128 diagonal tile held in shared memory and leaves the four diagonal
+// 32 x 32 blocks of its inverse; k_tile_inv (same shared-memory layout) completes inverse tiles off the critical path.
+// Blocked with 32 x 32 blocks so that only 4 x 16 column-pair steps are sequential:
+//   per block column kb: warp 0 factors the 32 x 32 diagonal block in registers (lane = row, column pairs, the pivot
+//   chain by shuffles), warp 1 inverts it behind warp 0; the panel  L_ik = A_ik inv(L_kk)^T  and the trailing update
+//   A_ij -= L_ik L_jk^T  are 8 x 32 strips of FP64 MMAs (DMMA) out of shared memory -- the part the next diagonal block
+//   needs by warps 0-3 alone on the tensor pipe, the rest by background warps underneath the next factorisation.
+//   k_tile_inv: the two 64 x 64 diagonal halves from their 32-blocks, then W21 = -W22 (L21 W11); the (unused) upper-right
 //   64 x 64 quadrant of the tile is the scratch for L21 W11.
 constexpr int PT = 128;
 constexpr int PLD = PT + 4;   // 132 = 4 mod 16: conflict-free DMMA fragment loads in both orientations
 constexpr int SLD = 36;       // 32 x 32 scratch blocks, same residue
-constexpr int N_SCRATCH = 6;  // inv(L_kk) x 4, two temporaries
+constexpr int N_SCRATCH = 6;  // inv(L_kk) x 4, two temporaries (k_tile_inv)
 constexpr int POTF2_SMEM = (PT * PLD + N_SCRATCH * 32 * SLD + 2 * 32 * 4 + 32 + 16) * (int)sizeof(double);
 
 // C(8 x 32 strip) = (accumulate ? C : 0) + alpha * sum_k A(row, k) * Bop(col, k);  Bop(col,k) = B_KN ? B[k][col] : B[col][k].
