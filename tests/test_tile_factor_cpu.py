@@ -127,3 +127,27 @@ def test_block_substitution_with_refinement_is_backward_stable():
     assert backward(X_ref) <= 1e-14
     assert backward(X_blk) <= 5.0 * max(backward(X_ref), 2.0 ** -52)
     assert backward(X_inv) >= 100.0 * backward(X_blk)          # what the refinement and the small blocks buy
+
+
+def tile_inverse(L, W_diag):
+    """k_tile_inv: the inverse of a 128 x 128 lower factor from its four inverted diagonal 32-blocks -- first the two 64 x 64
+    diagonal halves (W_ba = -W_b (L_ba W_a)), then W21 = -W22 (L21 W11)."""
+    W = np.zeros((128, 128))
+    for h in range(2):
+        a, b = slice(64 * h, 64 * h + 32), slice(64 * h + 32, 64 * h + 64)
+        W[a, a], W[b, b] = W_diag[2 * h], W_diag[2 * h + 1]
+        W[b, a] = -W_diag[2 * h + 1] @ (L[b, a] @ W_diag[2 * h])
+    lo, hi = slice(0, 64), slice(64, 128)
+    T = L[hi, lo] @ W[lo, lo]
+    W[hi, lo] = -W[hi, hi] @ T
+    return W
+
+
+def test_tile_inverse_from_diagonal_blocks():
+    rng = np.random.default_rng(9)
+    X = rng.standard_normal((128, 160))
+    L = np.linalg.cholesky(X @ X.T / 128 + np.eye(128))
+    W_diag = [np.linalg.inv(L[32 * j:32 * j + 32, 32 * j:32 * j + 32]) for j in range(4)]
+    W = tile_inverse(L, W_diag)
+    assert np.max(np.abs(np.triu(W, 1))) == 0.0
+    assert np.max(np.abs(W @ L - np.eye(128))) <= 1e-13
